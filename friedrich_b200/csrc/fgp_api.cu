@@ -1,0 +1,688 @@
+// fgp_api.cu — C-ABI entry points of libfgp_sm100.so (see include/fgp.h for the contract and the reference
+// call sites each function replaces).  One handle = one GPU, one stream; there is no CPU fallback anywhere:
+// every numeric result below is produced by the CUDA kernels in this directory or the call fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/fgp.h"
+#include "common.cuh"
+#include "gemm_nt.cuh"
+#include "kernel_eval.cuh"
+#include "model.cuh"
+#include "pair_tiles.cuh"
+#include "potrf.cuh"
+#include "vector_kernels.cuh"
+#include "trsm.cuh"
+#include "lml.cuh"
+
+using namespace fgp;
+
+#define FGP_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+// upload a column-major host matrix (rows x cols, ld) compactly into m->staging (ld = rows)
+int upload_colmajor(fgp_model* m, const double* src, int64_t ld, int64_t rows, int64_t cols) {
+    CU(m, m->staging.reserve((size_t)rows * cols));
+    CU(m, cudaMemcpy2DAsync(m->staging.p, rows * sizeof(double), src, ld * sizeof(double), rows * sizeof(double), cols,
+                            cudaMemcpyHostToDevice, m->st));
+    return FGP_OK;
+}
+
+// ---- Gram / cross-covariance launch -----------------------------------------------------------------------------
+template <int KIND, int MODE>
+void launch_cov(const PairArgs& pa, const CovWriteEpi<KIND>& epi, cudaStream_t st) {
+    pair_tile_kernel<MODE, CovWriteEpi<KIND>><<<pair_grid(pa), 256, 0, st>>>(pa, epi);
+}
+
+void write_covariance(fgp_model* m, const KernelTraits& kt, const fgp_kernel_desc* kd, const PairArgs& pa, double* out,
+                      int64_t ld, int64_t valid_rows, int64_t valid_cols, double noise2) {
+    const DevKernel dk = to_dev(kd);
+    const int mode = (kt.need_d2 ? PAIR_D2 : 0) | (kt.need_dot ? PAIR_DOT : 0);
+    if (kt.kind == KIND_SQEXP) {
+        CovWriteEpi<KIND_SQEXP> e{dk, out, ld, valid_rows, valid_cols, pa.symmetric, noise2};
+        launch_cov<KIND_SQEXP, PAIR_D2>(pa, e, m->st);
+    } else if (kt.kind == KIND_MATERN2) {
+        CovWriteEpi<KIND_MATERN2> e{dk, out, ld, valid_rows, valid_cols, pa.symmetric, noise2};
+        launch_cov<KIND_MATERN2, PAIR_D2>(pa, e, m->st);
+    } else {
+        CovWriteEpi<KIND_GENERIC> e{dk, out, ld, valid_rows, valid_cols, pa.symmetric, noise2};
+        if (mode == PAIR_D2) launch_cov<KIND_GENERIC, PAIR_D2>(pa, e, m->st);
+        else if (mode == PAIR_DOT) launch_cov<KIND_GENERIC, PAIR_DOT>(pa, e, m->st);
+        else launch_cov<KIND_GENERIC, PAIR_BOTH>(pa, e, m->st);
+    }
+    m->launches += 1;
+}
+
+PairArgs train_pair_args(const fgp_model* m) {
+    PairArgs pa{};
+    pa.xa_c = pa.xb_c = m->xc.p;
+    pa.xa_r = pa.xb_r = m->xr.p;
+    pa.na = pa.nb = m->nc.p;
+    pa.dp = (int)m->dp;
+    pa.rows = pa.cols = m->np;
+    pa.row_tile0 = 0;
+    pa.symmetric = 1;
+    return pa;
+}
+
+// ---- alpha = K^-1 y : z = L^-1 y (kept for the likelihood, mod.rs:203), alpha = L^-T z --------------------------
+void solve_alpha(fgp_model* m) {
+    const int nb = (int)(m->np / TILE);
+    cudaMemcpyAsync(m->work.p, m->y.p, m->np * sizeof(double), cudaMemcpyDeviceToDevice, m->st);
+    for (int j = 0; j < nb; ++j) {
+        trsv_fwd_kernel<<<nb - j, 128, 0, m->st>>>(m->L.p, m->cap, m->inv.p, m->work.p, m->z.p, j);
+        m->launches += 1;
+    }
+    cudaMemcpyAsync(m->work.p, m->z.p, m->np * sizeof(double), cudaMemcpyDeviceToDevice, m->st);
+    for (int j = nb - 1; j >= 0; --j) {
+        trsv_adj_kernel<<<j + 1, 128, 0, m->st>>>(m->L.p, m->cap, m->invT.p, m->work.p, m->alpha.p, j, nb);
+        m->launches += 1;
+    }
+}
+
+int reserve_training(fgp_model* m, int64_t cap_rows, int64_t dp, bool keep) {
+    // `keep` is used by add_samples when the capacity grows: point arrays and vectors keep their prefix; L is handled by
+    // the caller (its leading dimension changes).
+    CU(m, m->xr.reserve((size_t)cap_rows * dp, keep, m->st));
+    CU(m, m->xc.reserve((size_t)cap_rows * dp, keep, m->st));
+    CU(m, m->nc.reserve((size_t)cap_rows, keep, m->st));
+    CU(m, m->nr.reserve((size_t)cap_rows, keep, m->st));
+    CU(m, m->cmean.reserve((size_t)std::max<int64_t>(dp, 8), keep, m->st));
+    CU(m, m->y.reserve((size_t)cap_rows, keep, m->st));
+    CU(m, m->z.reserve((size_t)cap_rows));
+    CU(m, m->alpha.reserve((size_t)cap_rows));
+    CU(m, m->work.reserve((size_t)cap_rows));
+    CU(m, m->inv.reserve((size_t)cap_rows * TILE));
+    CU(m, m->invT.reserve((size_t)cap_rows * TILE));
+    return FGP_OK;
+}
+
+// Gram lower triangle + noise^2 I (algebra/mod.rs:67-79), blocked Cholesky (algebra/mod.rs:81-91), alpha.
+int factor_resident(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& kt, double noise, int has_eps,
+                    double eps) {
+    CU(m, cudaMemsetAsync(m->info_d, 0, sizeof(int), m->st));
+    write_covariance(m, kt, kd, train_pair_args(m), m->L.p, m->cap, m->n, m->n, noise * noise);
+    PotrfCounters cnt;
+    potrf_lower(m->L.p, m->cap, m->np, 0, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->st, &cnt);
+    m->launches += cnt.launches;
+    CU(m, cudaMemcpyAsync(m->info_h, m->info_d, sizeof(int), cudaMemcpyDeviceToHost, m->st));
+    solve_alpha(m);
+    CU(m, cudaStreamSynchronize(m->st));
+    CU(m, cudaGetLastError());
+    if (*m->info_h != 0) {
+        m->failed_col = *m->info_h - 1;
+        m->fitted = false;
+        return fail(m, FGP_ERR_NOT_POSDEF,
+                    "Cholesky decomposition failed at column " + std::to_string(m->failed_col));
+    }
+    m->failed_col = -1;
+    m->fitted = true;
+    return FGP_OK;
+}
+
+int check_kernel(fgp_model* m, const fgp_kernel_desc* kd, KernelTraits* kt) {
+    *kt = classify(kd);
+    if (!kt->valid) return fail(m, FGP_ERR_BAD_KERNEL, "malformed or unsupported kernel descriptor");
+    return FGP_OK;
+}
+
+int stage_queries(fgp_model* m, const double* Xq, int64_t ldq, int64_t q) {
+    if (!m->fitted) return fail(m, FGP_ERR_NOT_FITTED, "model is not fitted");
+    if (!Xq || q <= 0 || ldq < q) return fail(m, FGP_ERR_BAD_ARG, "bad query matrix");
+    const int64_t qp = round_up(q, TILE);
+    FGP_TRY(upload_colmajor(m, Xq, ldq, q, m->d));
+    CU(m, m->qr.reserve((size_t)qp * m->dp));
+    CU(m, m->qc.reserve((size_t)qp * m->dp));
+    CU(m, m->qnc.reserve((size_t)qp));
+    CU(m, m->qnr.reserve((size_t)qp));
+    CU(m, m->bt.reserve((size_t)qp * m->np));
+    CU(m, m->partial.reserve((size_t)(m->np / ROWRED_CHUNK) * qp));
+    CU(m, m->mean_d.reserve((size_t)qp));
+    CU(m, m->var_d.reserve((size_t)qp));
+    convert_points_kernel<<<(unsigned)((qp + 255) / 256), 256, 0, m->st>>>(m->staging.p, q, q, (int)m->d, (int)m->dp,
+                                                                          m->cmean.p, 0, qp, m->qr.p, m->qc.p, m->qnc.p,
+                                                                          m->qnr.p);
+    m->launches += 1;
+    m->q = q;
+    m->qp = qp;
+    m->have_mean = m->have_var = false;
+    return FGP_OK;
+}
+
+PairArgs query_pair_args(const fgp_model* m) {
+    PairArgs pa{};
+    pa.xa_c = m->qc.p;
+    pa.xa_r = m->qr.p;
+    pa.na = m->qnc.p;
+    pa.xb_c = m->xc.p;
+    pa.xb_r = m->xr.p;
+    pa.nb = m->nc.p;
+    pa.dp = (int)m->dp;
+    pa.rows = m->qp;
+    pa.cols = m->np;
+    pa.row_tile0 = 0;
+    pa.symmetric = 0;
+    return pa;
+}
+
+// Device part of predict / predict_variance / predict_mean_variance on the staged queries.
+//   Bt (qp x np) = k(query, train)                     make_covariance_matrix, algebra/mod.rs:41-54 (transposed)
+//   mean = Bt * alpha                                   == (K^-1 K_nq)^T y  (mod.rs:235,241) with alpha = K^-1 y cached
+//   Bt <- Bt * L^-T                                     l().solve_lower_triangular (mod.rs:260-263), transposed
+//   var_i = k(q_i,q_i) - || Bt[i,:] ||^2                mod.rs:266-270
+int predict_device(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& kt, int want_mean, int want_var) {
+    const int64_t qp = m->qp, np = m->np;
+    write_covariance(m, kt, kd, query_pair_args(m), m->bt.p, qp, m->q, m->n, 0.0);
+    const dim3 rgrid((unsigned)(qp / 128), (unsigned)(np / ROWRED_CHUNK));
+    const int chunks = (int)(np / ROWRED_CHUNK);
+    const DevKernel dk = to_dev(kd);
+    if (want_mean) {
+        rowreduce_partial_kernel<0><<<rgrid, 128, 0, m->st>>>(m->bt.p, qp, m->alpha.p, m->partial.p, qp);
+        rowreduce_final_kernel<<<(unsigned)(qp / 128), 128, 0, m->st>>>(m->partial.p, chunks, qp, m->q, 0, dk, m->qnr.p,
+                                                                         m->mean_d.p);
+        m->launches += 2;
+        m->have_mean = true;
+    }
+    if (want_var) {
+        m->launches += trsm_fwd_t(m->bt.p, qp, qp, m->L.p, m->cap, m->inv.p, 0, np / TILE, nullptr, m->st);
+        rowreduce_partial_kernel<1><<<rgrid, 128, 0, m->st>>>(m->bt.p, qp, nullptr, m->partial.p, qp);
+        rowreduce_final_kernel<<<(unsigned)(qp / 128), 128, 0, m->st>>>(m->partial.p, chunks, qp, m->q, 1, dk, m->qnr.p,
+                                                                         m->var_d.p);
+        m->launches += 2;
+        m->have_var = true;
+    }
+    return FGP_OK;
+}
+
+int fetch_predictions(fgp_model* m, double* mean, double* var) {
+    FGP_TRY(ensure_pinned(m, (size_t)2 * m->qp));
+    if (mean) {
+        if (!m->have_mean) return fail(m, FGP_ERR_BAD_ARG, "mean was not computed");
+        CU(m, cudaMemcpyAsync(m->pinned, m->mean_d.p, m->q * sizeof(double), cudaMemcpyDeviceToHost, m->st));
+    }
+    if (var) {
+        if (!m->have_var) return fail(m, FGP_ERR_BAD_ARG, "variance was not computed");
+        CU(m, cudaMemcpyAsync(m->pinned + m->qp, m->var_d.p, m->q * sizeof(double), cudaMemcpyDeviceToHost, m->st));
+    }
+    CU(m, cudaStreamSynchronize(m->st));
+    if (mean) std::memcpy(mean, m->pinned, m->q * sizeof(double));
+    if (var) std::memcpy(var, m->pinned + m->qp, m->q * sizeof(double));
+    return FGP_OK;
+}
+
+int predict_common(fgp_model* m, const fgp_kernel_desc* kd, const double* Xq, int64_t ldq, int64_t q, double* mean,
+                   double* var) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    KernelTraits kt;
+    FGP_TRY(check_kernel(m, kd, &kt));
+    if (!mean && !var) return fail(m, FGP_ERR_BAD_ARG, "no output buffer");
+    begin_timed(m);
+    FGP_TRY(stage_queries(m, Xq, ldq, q));
+    FGP_TRY(predict_device(m, kd, kt, mean != nullptr, var != nullptr));
+    FGP_TRY(end_timed(m));
+    return fetch_predictions(m, mean, var);
+}
+
+}  // namespace
+
+// =================================================================================================================
+// lifecycle
+FGP_EXPORT const char* fgp_version(void) { return "libfgp_sm100 0.1 (sm_100a, fp64 DMMA + TMA)"; }
+
+FGP_EXPORT int fgp_create(int device, fgp_model** out) {
+    if (!out) return FGP_ERR_BAD_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return FGP_ERR_CUDA;
+    fgp_model* m = new (std::nothrow) fgp_model();
+    if (!m) return FGP_ERR_CUDA;
+    m->device = device;
+    DeviceGuard dg(device);
+    bool ok = cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&m->st2, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreate(&m->ev0) == cudaSuccess && cudaEventCreate(&m->ev1) == cudaSuccess &&
+              cudaEventCreateWithFlags(&m->evA, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&m->evB, cudaEventDisableTiming) == cudaSuccess &&
+              cudaMalloc(&m->info_d, sizeof(int)) == cudaSuccess &&
+              cudaMallocHost(&m->info_h, sizeof(int)) == cudaSuccess && potrf_prepare() == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        fgp_destroy(m);
+        return FGP_ERR_CUDA;
+    }
+    *out = m;
+    return FGP_OK;
+}
+
+FGP_EXPORT int fgp_destroy(fgp_model* m) {
+    if (!m) return FGP_OK;
+    {
+        DeviceGuard dg(m->device);
+        if (m->st) cudaStreamSynchronize(m->st);
+        if (m->st2) cudaStreamSynchronize(m->st2);
+        for (DevBuf* b : {&m->xr, &m->xc, &m->nc, &m->nr, &m->cmean, &m->y, &m->z, &m->alpha, &m->work, &m->L, &m->inv,
+                          &m->invT, &m->staging, &m->qr, &m->qc, &m->qnc, &m->qnr, &m->bt, &m->partial, &m->mean_d,
+                          &m->var_d, &m->scalars, &m->kqq, &m->U, &m->Kinv, &m->lml_partial})
+            b->release();
+        if (m->info_d) cudaFree(m->info_d);
+        if (m->info_h) cudaFreeHost(m->info_h);
+        if (m->pinned) cudaFreeHost(m->pinned);
+        if (m->ev0) cudaEventDestroy(m->ev0);
+        if (m->ev1) cudaEventDestroy(m->ev1);
+        if (m->evA) cudaEventDestroy(m->evA);
+        if (m->evB) cudaEventDestroy(m->evB);
+        if (m->st) cudaStreamDestroy(m->st);
+        if (m->st2) cudaStreamDestroy(m->st2);
+    }
+    delete m;
+    return FGP_OK;
+}
+
+FGP_EXPORT const char* fgp_last_error(const fgp_model* m) { return m ? m->err.c_str() : "null handle"; }
+FGP_EXPORT int64_t fgp_failed_column(const fgp_model* m) { return m ? m->failed_col : -1; }
+FGP_EXPORT int64_t fgp_num_samples(const fgp_model* m) { return m ? m->n : 0; }
+FGP_EXPORT int64_t fgp_num_dims(const fgp_model* m) { return m ? m->d : 0; }
+FGP_EXPORT double fgp_last_device_ms(const fgp_model* m) { return m ? (double)m->last_ms : 0.0; }
+FGP_EXPORT int64_t fgp_last_launch_count(const fgp_model* m) { return m ? m->launches : 0; }
+
+FGP_EXPORT void* fgp_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+FGP_EXPORT void fgp_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+// =================================================================================================================
+// fit
+namespace {
+// EMatrix::new + Input::into_dmatrix (mod.rs:142-148): make the training inputs resident (row-major, padded, centred)
+int set_inputs(fgp_model* m, const double* X, int64_t ldx, int64_t n, int64_t d) {
+    if (!X || n <= 0 || d <= 0 || ldx < n) return fail(m, FGP_ERR_BAD_ARG, "bad training matrix");
+    m->fitted = false;
+    const int64_t np = round_up(n, TILE), dp = round_up(d, 4);
+    if (np > m->cap || dp != m->dp) {
+        const int64_t cap = std::max(np, m->cap);
+        FGP_TRY(reserve_training(m, cap, dp, false));
+        CU(m, m->L.reserve((size_t)cap * cap));
+        m->cap = cap;
+    }
+    m->n = n;
+    m->d = d;
+    m->dp = dp;
+    m->np = np;
+    FGP_TRY(upload_colmajor(m, X, ldx, n, d));
+    col_mean_kernel<<<(unsigned)d, 256, 0, m->st>>>(m->staging.p, n, n, m->cmean.p);
+    convert_points_kernel<<<(unsigned)((np + 255) / 256), 256, 0, m->st>>>(m->staging.p, n, n, (int)d, (int)dp, m->cmean.p,
+                                                                          0, np, m->xr.p, m->xc.p, m->nc.p, m->nr.p);
+    m->launches += 2;
+    CU(m, cudaMemsetAsync(m->y.p, 0, np * sizeof(double), m->st));
+    return FGP_OK;
+}
+}  // namespace
+
+FGP_EXPORT int fgp_set_inputs(fgp_model* m, const double* X, int64_t ldx, int64_t n, int64_t d) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    begin_timed(m);
+    FGP_TRY(set_inputs(m, X, ldx, n, d));
+    return end_timed(m);
+}
+
+FGP_EXPORT int fgp_fit(fgp_model* m, const double* X, int64_t ldx, int64_t n, int64_t d, const double* y_resid,
+                       const fgp_kernel_desc* kernel, double noise, int has_eps, double eps) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (!y_resid) return fail(m, FGP_ERR_BAD_ARG, "null training outputs");
+    if (!(noise >= 0.0)) return fail(m, FGP_ERR_BAD_ARG, "The noise parameter should non-negative");  // mod.rs:150
+    KernelTraits kt;
+    FGP_TRY(check_kernel(m, kernel, &kt));
+    begin_timed(m);
+    FGP_TRY(set_inputs(m, X, ldx, n, d));
+    CU(m, cudaMemcpyAsync(m->y.p, y_resid, n * sizeof(double), cudaMemcpyHostToDevice, m->st));
+    int rc = factor_resident(m, kernel, kt, noise, has_eps, eps);
+    int rc2 = end_timed(m);
+    return rc != FGP_OK ? rc : rc2;
+}
+
+FGP_EXPORT int fgp_refit(fgp_model* m, const fgp_kernel_desc* kernel, double noise, int has_eps, double eps) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (m->n <= 0) return fail(m, FGP_ERR_NOT_FITTED, "no resident training set");
+    if (!(noise >= 0.0)) return fail(m, FGP_ERR_BAD_ARG, "The noise parameter should non-negative");
+    KernelTraits kt;
+    FGP_TRY(check_kernel(m, kernel, &kt));
+    begin_timed(m);
+    int rc = factor_resident(m, kernel, kt, noise, has_eps, eps);
+    int rc2 = end_timed(m);
+    return rc != FGP_OK ? rc : rc2;
+}
+
+FGP_EXPORT int fgp_set_outputs(fgp_model* m, const double* y_resid, int64_t n) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (m->n <= 0) return fail(m, FGP_ERR_NOT_FITTED, "no resident training set");
+    if (!y_resid || n != m->n) return fail(m, FGP_ERR_BAD_ARG, "output vector length mismatch");
+    begin_timed(m);
+    CU(m, cudaMemcpyAsync(m->y.p, y_resid, n * sizeof(double), cudaMemcpyHostToDevice, m->st));
+    if (m->fitted) solve_alpha(m);
+    return end_timed(m);
+}
+
+// =================================================================================================================
+// predict
+FGP_EXPORT int fgp_predict_mean(fgp_model* m, const fgp_kernel_desc* kernel, const double* Xq, int64_t ldq, int64_t q,
+                                double* mean_wo_prior) {
+    if (!mean_wo_prior) return m ? fail(m, FGP_ERR_BAD_ARG, "null output") : FGP_ERR_BAD_ARG;
+    return predict_common(m, kernel, Xq, ldq, q, mean_wo_prior, nullptr);
+}
+FGP_EXPORT int fgp_predict_var(fgp_model* m, const fgp_kernel_desc* kernel, const double* Xq, int64_t ldq, int64_t q,
+                               double* var) {
+    if (!var) return m ? fail(m, FGP_ERR_BAD_ARG, "null output") : FGP_ERR_BAD_ARG;
+    return predict_common(m, kernel, Xq, ldq, q, nullptr, var);
+}
+FGP_EXPORT int fgp_predict_mean_var(fgp_model* m, const fgp_kernel_desc* kernel, const double* Xq, int64_t ldq, int64_t q,
+                                    double* mean_wo_prior, double* var) {
+    if (!var || !mean_wo_prior) return m ? fail(m, FGP_ERR_BAD_ARG, "null output") : FGP_ERR_BAD_ARG;
+    return predict_common(m, kernel, Xq, ldq, q, mean_wo_prior, var);
+}
+
+FGP_EXPORT int fgp_stage_queries(fgp_model* m, const double* Xq, int64_t ldq, int64_t q) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    begin_timed(m);
+    FGP_TRY(stage_queries(m, Xq, ldq, q));
+    return end_timed(m);
+}
+FGP_EXPORT int fgp_predict_staged(fgp_model* m, const fgp_kernel_desc* kernel, int want_mean, int want_var) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (!m->fitted || m->q <= 0) return fail(m, FGP_ERR_NOT_FITTED, "no staged queries");
+    KernelTraits kt;
+    FGP_TRY(check_kernel(m, kernel, &kt));
+    begin_timed(m);
+    FGP_TRY(predict_device(m, kernel, kt, want_mean, want_var));
+    return end_timed(m);
+}
+FGP_EXPORT int fgp_fetch_predictions(fgp_model* m, double* mean_wo_prior, double* var) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (m->q <= 0) return fail(m, FGP_ERR_NOT_FITTED, "no staged queries");
+    return fetch_predictions(m, mean_wo_prior, var);
+}
+
+// predict_covariance (mod.rs:329-350): Kqq - kl^T kl ; sample_at (mod.rs:371-384): Kqq - Knq^T (K^-1 Knq).
+// Both are the same matrix; on the device it is formed once as Kqq - Bt Bt^T with Bt = (L^-1 Knq)^T.
+FGP_EXPORT int fgp_predict_cov(fgp_model* m, const fgp_kernel_desc* kernel, const double* Xq, int64_t ldq, int64_t q,
+                               int mode, double* cov, int64_t ldc, double* mean_wo_prior) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (!cov || ldc < q || (mode != 0 && mode != 1)) return fail(m, FGP_ERR_BAD_ARG, "bad covariance output");
+    KernelTraits kt;
+    FGP_TRY(check_kernel(m, kernel, &kt));
+    begin_timed(m);
+    FGP_TRY(stage_queries(m, Xq, ldq, q));
+    FGP_TRY(predict_device(m, kernel, kt, mean_wo_prior != nullptr, 1));
+    const int64_t qp = m->qp;
+    CU(m, m->kqq.reserve((size_t)qp * qp));
+    PairArgs pa = query_pair_args(m);
+    pa.xb_c = m->qc.p;
+    pa.xb_r = m->qr.p;
+    pa.nb = m->qnc.p;
+    pa.cols = qp;
+    write_covariance(m, kt, kernel, pa, m->kqq.p, qp, q, q, 0.0);
+    GemmArgs g{};
+    g.C = m->kqq.p; g.ldc = qp;
+    g.A = m->bt.p; g.lda = qp;
+    g.B = m->bt.p; g.ldb = qp;
+    g.M = g.N = (int)qp; g.K = (int)m->np;
+    g.alpha = -1.0; g.beta_one = 1; g.lower = 0; g.k_from_tile = 0;
+    m->launches += gemm_nt_launch(g, m->st) > 0;
+    FGP_TRY(end_timed(m));
+    // q x q result straight into the caller's buffer
+    CU(m, cudaMemcpy2DAsync(cov, ldc * sizeof(double), m->kqq.p, qp * sizeof(double), q * sizeof(double), q,
+                            cudaMemcpyDeviceToHost, m->st));
+    CU(m, cudaStreamSynchronize(m->st));
+    if (mean_wo_prior) return fetch_predictions(m, mean_wo_prior, nullptr);
+    return FGP_OK;
+}
+
+// =================================================================================================================
+// model selection
+FGP_EXPORT int fgp_likelihood(fgp_model* m, const fgp_kernel_desc* kernel, double noise, double* out) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (!m->fitted) return fail(m, FGP_ERR_NOT_FITTED, "model is not fitted");
+    if (!out) return fail(m, FGP_ERR_BAD_ARG, "null output");
+    KernelTraits kt;
+    FGP_TRY(check_kernel(m, kernel, &kt));
+    begin_timed(m);
+    CU(m, m->scalars.reserve(8));
+    const DevKernel dk = to_dev(kernel);
+    reduce_kernel<0><<<1, 256, 0, m->st>>>(m->z.p, nullptr, m->n, dk, 0.0, m->scalars.p);                 // ||L^-1 y||^2
+    reduce_kernel<1><<<1, 256, 0, m->st>>>(m->nr.p, nullptr, m->n, dk, noise * noise, m->scalars.p + 1);  // mod.rs:208-213
+    m->launches += 2;
+    FGP_TRY(ensure_pinned(m, 8));
+    CU(m, cudaMemcpyAsync(m->pinned, m->scalars.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, m->st));
+    FGP_TRY(end_timed(m));
+    const double data_fit = m->pinned[0], penalty = m->pinned[1];
+    const double norm = (double)m->n * std::log(2.0 * M_PI);
+    *out = -(data_fit + penalty + norm) / 2.0;  // mod.rs:216-219
+    return FGP_OK;
+}
+
+FGP_EXPORT int fgp_lml_gradient(fgp_model* m, const fgp_kernel_desc* kernel, double noise, int scaled, double* scale_out,
+                                double* grads) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (!m->fitted) return fail(m, FGP_ERR_NOT_FITTED, "model is not fitted");
+    if (!grads) return fail(m, FGP_ERR_BAD_ARG, "null output");
+    KernelTraits kt;
+    FGP_TRY(check_kernel(m, kernel, &kt));
+    begin_timed(m);
+    int rc = lml_gradient_device(m, kernel, kt, noise, scaled, scale_out, grads);
+    int rc2 = end_timed(m);
+    return rc != FGP_OK ? rc : rc2;
+}
+
+FGP_EXPORT int fgp_mean_pair_distance(fgp_model* m, double* out) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (m->n <= 0) return fail(m, FGP_ERR_NOT_FITTED, "no resident training set");
+    if (!out) return fail(m, FGP_ERR_BAD_ARG, "null output");
+    begin_timed(m);
+    int rc = mean_pair_distance_device(m, out);
+    int rc2 = end_timed(m);
+    return rc != FGP_OK ? rc : rc2;
+}
+
+// =================================================================================================================
+// state transfer
+FGP_EXPORT int fgp_download_factor(fgp_model* m, double* L, int64_t ldl) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (!m->fitted) return fail(m, FGP_ERR_NOT_FITTED, "model is not fitted");
+    if (!L || ldl < m->n) return fail(m, FGP_ERR_BAD_ARG, "bad factor buffer");
+    const int64_t n = m->n;
+    CU(m, cudaMemcpy2DAsync(L, ldl * sizeof(double), m->L.p, m->cap * sizeof(double), n * sizeof(double), n,
+                            cudaMemcpyDeviceToHost, m->st));
+    CU(m, cudaStreamSynchronize(m->st));
+    const double nanv = std::numeric_limits<double>::quiet_NaN();  // algebra/mod.rs:67: the upper triangle is never written
+    for (int64_t c = 1; c < n; ++c)
+        for (int64_t r = 0; r < c; ++r) L[r + c * ldl] = nanv;
+    return FGP_OK;
+}
+
+FGP_EXPORT int fgp_download_alpha(fgp_model* m, double* alpha) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (!m->fitted) return fail(m, FGP_ERR_NOT_FITTED, "model is not fitted");
+    if (!alpha) return fail(m, FGP_ERR_BAD_ARG, "null output");
+    CU(m, cudaMemcpyAsync(alpha, m->alpha.p, m->n * sizeof(double), cudaMemcpyDeviceToHost, m->st));
+    CU(m, cudaStreamSynchronize(m->st));
+    return FGP_OK;
+}
+
+// =================================================================================================================
+// add_samples (mod.rs:173-190 + algebra/mod.rs:97-126)
+FGP_EXPORT int fgp_add_samples(fgp_model* m, const double* Xnew, int64_t ldx, int64_t k, const double* ynew_resid,
+                               const fgp_kernel_desc* kernel, double noise, int has_eps, double eps) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (!m->fitted) return fail(m, FGP_ERR_NOT_FITTED, "model is not fitted");
+    if (!Xnew || !ynew_resid || k <= 0 || ldx < k) return fail(m, FGP_ERR_BAD_ARG, "bad sample matrix");
+    if (!(noise >= 0.0)) return fail(m, FGP_ERR_BAD_ARG, "The noise parameter should non-negative");
+    KernelTraits kt;
+    FGP_TRY(check_kernel(m, kernel, &kt));
+    begin_timed(m);
+    const int64_t n_old = m->n, n_new = n_old + k, np_new = round_up(n_new, TILE);
+    // --- capacity (EMatrix::add_rows grows by x1.5, extendable_matrix.rs:30-49) -------------------------------
+    if (np_new > m->cap) {
+        const int64_t cap_new = std::max(np_new, round_up(m->cap + m->cap / 2, TILE));
+        FGP_TRY(reserve_training(m, cap_new, m->dp, true));
+        DevBuf Lnew;
+        CU(m, Lnew.reserve((size_t)cap_new * cap_new));
+        CU(m, cudaMemcpy2DAsync(Lnew.p, cap_new * sizeof(double), m->L.p, m->cap * sizeof(double), m->np * sizeof(double),
+                                m->np, cudaMemcpyDeviceToDevice, m->st));
+        CU(m, cudaStreamSynchronize(m->st));
+        m->L.release();
+        m->L = Lnew;
+        m->cap = cap_new;
+    }
+    // --- new points: same centring as the resident ones (cmean is only a numerical shift, any value is valid) ---
+    FGP_TRY(upload_colmajor(m, Xnew, ldx, k, m->d));
+    convert_points_kernel<<<(unsigned)((np_new - n_old + 255) / 256), 256, 0, m->st>>>(
+        m->staging.p, k, k, (int)m->d, (int)m->dp, m->cmean.p, n_old, np_new - n_old, m->xr.p, m->xc.p, m->nc.p, m->nr.p);
+    m->launches += 1;
+    CU(m, cudaMemsetAsync(m->y.p + n_old, 0, (np_new - n_old) * sizeof(double), m->st));
+    CU(m, cudaMemcpyAsync(m->y.p + n_old, ynew_resid, k * sizeof(double), cudaMemcpyHostToDevice, m->st));
+    // --- block rows >= jb are (re)built: Gram rows, forward solve against the frozen block columns, trailing potrf ---
+    const int64_t jb = n_old / TILE;  // first block column touched by the new rows
+    m->n = n_new;
+    m->np = np_new;
+    CU(m, cudaMemsetAsync(m->info_d, 0, sizeof(int), m->st));
+    PairArgs pa = train_pair_args(m);
+    pa.row_tile0 = (int)jb;
+    write_covariance(m, kt, kernel, pa, m->L.p, m->cap, n_new, n_new, noise * noise);
+    // rows [jb*128, np_new) x columns [0, jb*128):  A <- A * L11^-T, and the trailing block gets -= A A^T
+    double* Arows = m->L.p + jb * TILE;  // row offset inside every column
+    m->launches += trsm_fwd_t(Arows, m->cap, np_new - jb * TILE, m->L.p, m->cap, m->inv.p, 0, jb, Arows + jb * TILE * m->cap,
+                              m->st);
+    PotrfCounters cnt;
+    potrf_lower(m->L.p, m->cap, np_new, jb, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->st, &cnt);
+    m->launches += cnt.launches;
+    CU(m, cudaMemcpyAsync(m->info_h, m->info_d, sizeof(int), cudaMemcpyDeviceToHost, m->st));
+    solve_alpha(m);
+    int rc2 = end_timed(m);
+    if (rc2 != FGP_OK) return rc2;
+    if (*m->info_h != 0) {
+        m->failed_col = *m->info_h - 1;
+        m->fitted = false;
+        return fail(m, FGP_ERR_NOT_POSDEF, "Cholesky update failed at column " + std::to_string(m->failed_col));
+    }
+    return FGP_OK;
+}
+
+// =================================================================================================================
+// Cholesky of a caller-supplied SPD matrix with the same device factorisation (MultivariateNormal::new,
+// multivariate_normal.rs:54-59: `covariance.cholesky().expect(..).unpack()`): A (n x n column-major, lower triangle
+// read) is overwritten by L with the strict upper triangle zeroed (unpack()).
+FGP_EXPORT int fgp_cholesky_lower(int device, double* A, int64_t lda, int64_t n, int64_t* failed_col) {
+    if (!A || n <= 0 || lda < n) return FGP_ERR_BAD_ARG;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return FGP_ERR_CUDA;
+    DeviceGuard dg(device);
+    if (potrf_prepare() != cudaSuccess) return FGP_ERR_CUDA;
+    const int64_t np = round_up(n, TILE);
+    double *dA = nullptr, *dinv = nullptr;
+    int* dinfo = nullptr;
+    int info = 0;
+    int rc = FGP_OK;
+    if (cudaMalloc(&dA, (size_t)np * np * 8) != cudaSuccess || cudaMalloc(&dinv, (size_t)2 * np * TILE * 8) != cudaSuccess ||
+        cudaMalloc(&dinfo, sizeof(int)) != cudaSuccess)
+        rc = FGP_ERR_CUDA;
+    if (rc == FGP_OK) {
+        cudaMemsetAsync(dA, 0, (size_t)np * np * 8, 0);
+        cudaMemsetAsync(dinfo, 0, sizeof(int), 0);
+        set_identity_kernel<<<(unsigned)((np + 255) / 256), 256>>>(dA, np, np);  // padding block = I
+        cudaMemcpy2DAsync(dA, (size_t)np * 8, A, (size_t)lda * 8, (size_t)n * 8, n, cudaMemcpyHostToDevice, 0);
+        PotrfCounters cnt;
+        potrf_lower(dA, np, np, 0, dinv, dinv + np * TILE, 0, 0.0, dinfo, 0, &cnt);
+        cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, 0);
+        cudaMemcpy2DAsync(A, (size_t)lda * 8, dA, (size_t)np * 8, (size_t)n * 8, n, cudaMemcpyDeviceToHost, 0);
+        if (cudaStreamSynchronize(0) != cudaSuccess) rc = FGP_ERR_CUDA;
+    }
+    cudaFree(dA);
+    cudaFree(dinv);
+    cudaFree(dinfo);
+    if (cudaGetLastError() != cudaSuccess) rc = FGP_ERR_CUDA;
+    if (rc != FGP_OK) return rc;
+    if (failed_col) *failed_col = info ? info - 1 : -1;
+    if (info) return FGP_ERR_NOT_POSDEF;
+    for (int64_t c = 1; c < n; ++c)
+        for (int64_t r = 0; r < c; ++r) A[r + c * lda] = 0.0;
+    return FGP_OK;
+}
+
+// =================================================================================================================
+// test hook: the production GEMM on host matrices
+FGP_EXPORT int fgp_dbg_gemm_nt(int device, double* C, int64_t ldc, const double* A, int64_t lda, const double* B,
+                               int64_t ldb, int M, int N, int K, double alpha, int beta_one, int lower) {
+    if (M % GEMM_BM || N % GEMM_BN || K % GEMM_KC) return FGP_ERR_BAD_ARG;
+    DeviceGuard dg(device);
+    if (gemm_nt_prepare() != cudaSuccess) return FGP_ERR_CUDA;
+    double *dC = nullptr, *dA = nullptr, *dB = nullptr;
+    int rc = FGP_OK;
+    if (cudaMalloc(&dC, (size_t)M * N * 8) != cudaSuccess || cudaMalloc(&dA, (size_t)M * K * 8) != cudaSuccess ||
+        cudaMalloc(&dB, (size_t)N * K * 8) != cudaSuccess)
+        rc = FGP_ERR_CUDA;
+    if (rc == FGP_OK) {
+        cudaMemcpy2D(dC, (size_t)M * 8, C, (size_t)ldc * 8, (size_t)M * 8, N, cudaMemcpyHostToDevice);
+        cudaMemcpy2D(dA, (size_t)M * 8, A, (size_t)lda * 8, (size_t)M * 8, K, cudaMemcpyHostToDevice);
+        cudaMemcpy2D(dB, (size_t)N * 8, B, (size_t)ldb * 8, (size_t)N * 8, K, cudaMemcpyHostToDevice);
+        GemmArgs g{};
+        g.C = dC; g.ldc = M;
+        g.A = dA; g.lda = M;
+        g.B = dB; g.ldb = N;
+        g.M = M; g.N = N; g.K = K;
+        g.alpha = alpha; g.beta_one = beta_one; g.lower = lower; g.k_from_tile = 0;
+        gemm_nt_launch(g, 0);
+        if (cudaDeviceSynchronize() != cudaSuccess) rc = FGP_ERR_CUDA;
+        cudaMemcpy2D(C, (size_t)ldc * 8, dC, (size_t)M * 8, (size_t)M * 8, N, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(dC);
+    cudaFree(dA);
+    cudaFree(dB);
+    if (cudaGetLastError() != cudaSuccess) rc = FGP_ERR_CUDA;
+    return rc;
+}

@@ -1,0 +1,139 @@
+// model.cuh — the device-resident state behind an `fgp_model*` handle and the small host helpers every entry point
+// shares.  Mirrors the private fields of the reference's `GaussianProcess` (src/gaussian_process/mod.rs:58-79):
+// training_inputs (EMatrix, capacity-padded), training_outputs (EVector, already minus the prior) and
+// covmat_cholesky — plus what the device path caches on top (alpha = K^-1 y, z = L^-1 y, inverted diagonal blocks).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <mutex>
+#include <string>
+
+#include "../../include/fgp.h"
+#include "common.cuh"
+
+namespace fgp {
+
+struct DevBuf {
+    double* p = nullptr;
+    size_t cap = 0;  // in doubles
+    // grow-only; `keep` preserves the old contents (first `cap` doubles)
+    cudaError_t reserve(size_t n, bool keep = false, cudaStream_t st = 0) {
+        if (n <= cap) return cudaSuccess;
+        double* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, n * sizeof(double));
+        if (e != cudaSuccess) return e;
+        if (keep && p && cap) {
+            e = cudaMemcpyAsync(q, p, cap * sizeof(double), cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+        if (p) cudaFree(p);
+        p = q;
+        cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace fgp
+
+struct fgp_comm;  // multi-GPU transport (comm.cuh)
+
+struct fgp_model {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    cudaStream_t st2 = nullptr;  // look-ahead / copy stream
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
+    std::mutex mu;
+    std::string err;
+
+    // training state ------------------------------------------------------------------------------------------
+    bool fitted = false;
+    int64_t n = 0, d = 0, dp = 0, np = 0;  // samples, dims, padded dims (multiple of 4), padded samples (multiple of 128)
+    int64_t cap = 0;                       // capacity in rows (multiple of 128) = leading dimension of L
+    fgp::DevBuf xr, xc, nc, nr, cmean;     // raw / centred points [cap][dp], squared norms, column means [dp]
+    fgp::DevBuf y, z, alpha, work;         // outputs (0 padded), L^-1 y, K^-1 y, scratch vector
+    fgp::DevBuf L, inv, invT;              // factor [cap x cap], inverse diagonal blocks and their transposes
+    fgp::DevBuf staging;                   // H2D landing zone (column-major inputs)
+    int* info_d = nullptr;
+    int* info_h = nullptr;                 // pinned
+    int64_t failed_col = -1;
+
+    // query state ---------------------------------------------------------------------------------------------
+    int64_t q = 0, qp = 0;
+    fgp::DevBuf qr, qc, qnc, qnr;          // query points and norms
+    fgp::DevBuf bt;                        // transposed cross-covariance / solve buffer [qp x np]
+    fgp::DevBuf partial, mean_d, var_d, scalars, kqq;
+    double* pinned = nullptr;              // host staging for results
+    size_t pinned_cap = 0;
+    bool have_mean = false, have_var = false;
+
+    // LML workspace -------------------------------------------------------------------------------------------
+    fgp::DevBuf U, Kinv, lml_partial;
+
+    // multi-GPU -----------------------------------------------------------------------------------------------
+    fgp_comm* comm = nullptr;
+
+    // measurement ---------------------------------------------------------------------------------------------
+    float last_ms = 0.f;
+    int64_t launches = 0;
+};
+
+namespace fgp {
+
+inline int fail(fgp_model* m, int code, const std::string& msg) {
+    if (m) m->err = msg;
+    return code;
+}
+
+#define CU(m, call)                                                                                                 \
+    do {                                                                                                            \
+        cudaError_t e__ = (call);                                                                                   \
+        if (e__ != cudaSuccess)                                                                                     \
+            return fgp::fail(m, FGP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " (" __FILE__   \
+                                                  ":" + std::to_string(__LINE__) + ")");                             \
+    } while (0)
+
+#define FGP_TRY(expr)                   \
+    do {                                \
+        int rc__ = (expr);              \
+        if (rc__ != FGP_OK) return rc__; \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        cudaSetDevice(dev);
+    }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+inline int ensure_pinned(fgp_model* m, size_t doubles) {
+    if (doubles <= m->pinned_cap) return FGP_OK;
+    if (m->pinned) cudaFreeHost(m->pinned);
+    m->pinned = nullptr;
+    m->pinned_cap = 0;
+    CU(m, cudaMallocHost(&m->pinned, doubles * sizeof(double)));
+    m->pinned_cap = doubles;
+    return FGP_OK;
+}
+
+inline void begin_timed(fgp_model* m) {
+    m->launches = 0;
+    cudaEventRecord(m->ev0, m->st);
+}
+inline int end_timed(fgp_model* m) {
+    CU(m, cudaEventRecord(m->ev1, m->st));
+    CU(m, cudaEventSynchronize(m->ev1));
+    CU(m, cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
+    CU(m, cudaGetLastError());
+    return FGP_OK;
+}
+
+}  // namespace fgp

@@ -1,0 +1,135 @@
+/* fgp.h — C-ABI of libfgp_sm100.so: the B200 (sm_100a) replacement for friedrich's dense-algebra hot path.
+ *
+ * The reference (Rust crate friedrich v0.5.1) has no FFI; the seam this ABI replaces is the crate-private boundary
+ * between `gaussian_process` and `algebra` + nalgebra.  Each entry point below names the reference code it stands in
+ * for (paths relative to the reference root).  INTEGRATION.md shows the `extern "C"` block and the modified
+ * `algebra` module a friedrich maintainer would add.
+ *
+ * Conventions
+ *   - every matrix is f64, COLUMN-major with an explicit leading dimension (nalgebra DMatrix / EMatrix::as_matrix,
+ *     src/algebra/extendable_matrix.rs:52-55); inputs are n x d with one sample per ROW (src/conversion/mod.rs);
+ *   - the caller owns all host buffers; the handle owns all device memory; nothing is retained from host pointers;
+ *   - `y_resid` is training_outputs MINUS prior(X) (src/gaussian_process/mod.rs:156): priors stay on the host;
+ *   - every function returns an fgp_status; nothing aborts or throws across the boundary. The reference's panics
+ *     (src/algebra/mod.rs:85,90; src/gaussian_process/mod.rs:203,263,345) are mapped by the host shim;
+ *   - a handle is bound to one GPU and one host thread at a time (`&mut self` entry points: fit/refit/add_samples/
+ *     set_outputs; the `&self` ones — predict*, likelihood, lml_gradient — serialise on an internal mutex);
+ *   - there is NO CPU fallback: without a CUDA device fgp_create fails with FGP_ERR_CUDA.
+ */
+#ifndef FGP_H
+#define FGP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "fgp_kernel_desc.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fgp_model fgp_model; /* opaque: device X (row-major, padded), y, alpha, L, inverse diagonal blocks */
+
+typedef enum fgp_status {
+    FGP_OK = 0,
+    FGP_ERR_NOT_POSDEF = 1,   /* Cholesky pivot <= 0 / NaN and no valid substitute; see fgp_failed_column */
+    FGP_ERR_BAD_ARG = 2,      /* dimension mismatch, negative noise (mod.rs:150), null pointer ... */
+    FGP_ERR_BAD_KERNEL = 3,   /* malformed or unsupported kernel descriptor */
+    FGP_ERR_CUDA = 4,         /* CUDA runtime error (message in fgp_last_error) */
+    FGP_ERR_NOT_FITTED = 5,   /* predict/likelihood/... before fgp_fit */
+    FGP_ERR_COMM = 6          /* multi-GPU transport error */
+} fgp_status;
+
+/* lifecycle --------------------------------------------------------------------------------------------------- */
+int fgp_create(int device, fgp_model** out);
+int fgp_destroy(fgp_model* m);
+const char* fgp_last_error(const fgp_model* m);
+const char* fgp_version(void);
+
+/* fit ----------------------------------------------------------------------------------------------------------
+ * fgp_fit            make_cholesky_cov_matrix (src/algebra/mod.rs:59-92) as called by GaussianProcess::new
+ *                    (src/gaussian_process/mod.rs:158-159): uploads X (n x d, ld = ldx) and y_resid, assembles the
+ *                    Gram lower triangle + noise^2 I, factors it. has_eps/eps = cholesky_epsilon (mod.rs:67-73).
+ * fgp_set_inputs     EMatrix::new(training_inputs) only (mod.rs:147): makes X resident without fitting, so that the
+ *                    builder's heuristic_fit (builder.rs:193-196 -> fgp_mean_pair_distance) can run before the fit.
+ * fgp_refit          same as fgp_fit, on the X (and y) already resident (optimiser loops optimizer.rs:133-136, :267-270 and
+ *                    fit_parameters mod.rs:426-429).
+ * fgp_set_outputs    EVector::assign after a prior refit (mod.rs:420, extendable_matrix.rs:107-111).
+ * fgp_add_samples    EMatrix/EVector::add_rows + add_rows_cholesky_cov_matrix (mod.rs:181-189, algebra/mod.rs:97-126):
+ *                    k sequential insert_column(end) == block update of the factor; no failure check in the
+ *                    reference (sqrt of a negative gives NaN) — here a non-positive pivot returns FGP_ERR_NOT_POSDEF.
+ */
+int fgp_set_inputs(fgp_model* m, const double* X, int64_t ldx, int64_t n, int64_t d);
+int fgp_fit(fgp_model* m, const double* X, int64_t ldx, int64_t n, int64_t d, const double* y_resid,
+            const fgp_kernel_desc* kernel, double noise, int has_eps, double eps);
+int fgp_refit(fgp_model* m, const fgp_kernel_desc* kernel, double noise, int has_eps, double eps);
+int fgp_set_outputs(fgp_model* m, const double* y_resid, int64_t n);
+int fgp_add_samples(fgp_model* m, const double* Xnew, int64_t ldx, int64_t k, const double* ynew_resid,
+                    const fgp_kernel_desc* kernel, double noise, int has_eps, double eps);
+int64_t fgp_failed_column(const fgp_model* m); /* 0-based column of the failed pivot of the last fit, -1 if none */
+int64_t fgp_num_samples(const fgp_model* m);
+int64_t fgp_num_dims(const fgp_model* m);
+
+/* predict ------------------------------------------------------------------------------------------------------
+ * Xq is q x d (ld = ldq). Means are returned WITHOUT the prior (the shim adds prior(Xq), mod.rs:238-241).
+ * fgp_predict_mean      GaussianProcess::predict                 (mod.rs:226-244)
+ * fgp_predict_var       GaussianProcess::predict_variance        (mod.rs:248-273)
+ * fgp_predict_mean_var  GaussianProcess::predict_mean_variance   (mod.rs:290-326)
+ * fgp_predict_cov       predict_covariance (mode 0, mod.rs:329-350) / covariance of sample_at (mode 1, mod.rs:371-384);
+ *                       cov is q x q column-major, ld = ldc; mean_wo_prior may be NULL.
+ */
+int fgp_predict_mean(fgp_model* m, const fgp_kernel_desc* kernel, const double* Xq, int64_t ldq, int64_t q,
+                     double* mean_wo_prior);
+int fgp_predict_var(fgp_model* m, const fgp_kernel_desc* kernel, const double* Xq, int64_t ldq, int64_t q, double* var);
+int fgp_predict_mean_var(fgp_model* m, const fgp_kernel_desc* kernel, const double* Xq, int64_t ldq, int64_t q,
+                         double* mean_wo_prior, double* var);
+int fgp_predict_cov(fgp_model* m, const fgp_kernel_desc* kernel, const double* Xq, int64_t ldq, int64_t q, int mode,
+                    double* cov, int64_t ldc, double* mean_wo_prior);
+
+/* model selection ----------------------------------------------------------------------------------------------
+ * fgp_likelihood     GaussianProcess::likelihood (mod.rs:196-220), formula as coded (penalty is sum ln|k(x,x)+noise^2|).
+ * fgp_lml_gradient   scaled != 0: scaled_gradient_marginal_likelihood (optimizer.rs:159-203) -> *scale_out and P grads
+ *                    scaled == 0: gradient_marginal_likelihood (optimizer.rs:24-60) -> P grads followed by the noise grad.
+ *                    Replaces covmat_cholesky.inverse() + make_gradient_covariance_matrices (algebra/mod.rs:129-155);
+ *                    the P gradient matrices are never materialised.
+ * fgp_mean_pair_distance  fit_bandwidth_mean (src/parameters/kernel.rs:94-113) on the resident training inputs.
+ */
+int fgp_likelihood(fgp_model* m, const fgp_kernel_desc* kernel, double noise, double* out);
+int fgp_lml_gradient(fgp_model* m, const fgp_kernel_desc* kernel, double noise, int scaled, double* scale_out,
+                     double* grads);
+int fgp_mean_pair_distance(fgp_model* m, double* out);
+
+/* state transfer (serde feature, mod.rs:58; tests) --------------------------------------------------------------
+ * fgp_download_factor  L into a caller buffer, n x n column-major, strict upper triangle set to NaN exactly like
+ *                      the matrix nalgebra's Cholesky keeps (algebra/mod.rs:67).
+ * fgp_download_alpha   K^-1 y_resid (n values).
+ */
+int fgp_download_factor(fgp_model* m, double* L, int64_t ldl);
+int fgp_download_alpha(fgp_model* m, double* alpha);
+
+/* Cholesky of a caller-supplied SPD matrix with the same device factorisation: MultivariateNormal::new
+ * (src/gaussian_process/multivariate_normal.rs:54-59, `covariance.cholesky().expect(..).unpack()`). A is n x n
+ * column-major (lower triangle read) and is overwritten by L with the strict upper triangle zeroed. */
+int fgp_cholesky_lower(int device, double* A, int64_t lda, int64_t n, int64_t* failed_col);
+
+/* measurement --------------------------------------------------------------------------------------------------
+ * Device time (CUDA events on the model's stream) and number of kernel launches of the last entry-point call. */
+double fgp_last_device_ms(const fgp_model* m);
+int64_t fgp_last_launch_count(const fgp_model* m);
+/* Resident-input predict for kernel-only timing: stage queries once, then run the device part repeatedly. */
+int fgp_stage_queries(fgp_model* m, const double* Xq, int64_t ldq, int64_t q);
+int fgp_predict_staged(fgp_model* m, const fgp_kernel_desc* kernel, int want_mean, int want_var);
+int fgp_fetch_predictions(fgp_model* m, double* mean_wo_prior, double* var);
+
+/* page-locked host buffers for callers that want DMA-speed transfers (any host pointer is accepted everywhere) */
+void* fgp_alloc_pinned(size_t bytes);
+void fgp_free_pinned(void* p);
+
+/* test hook: C = beta*C + alpha*A*B^T on device copies of host matrices, through the production GEMM kernel */
+int fgp_dbg_gemm_nt(int device, double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb,
+                    int M, int N, int K, double alpha, int beta_one, int lower);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
