@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py — the hot path of friedrich on B200: GP fit (Gram + Cholesky, f64) TFLOP/s and predict queries/s.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload metric|c2|c4]
+
+One "step" = one pass of the fit hot path (Gram assembly + blocked Cholesky + alpha solve) over the synthetic training
+set of the workload.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how every field is produced.
+
+ * value          fit TFLOP/s, inputs resident in HBM (fgp_refit), device time from CUDA events on the library's stream
+ * e2e            same metric through the C-ABI with HOST (pinned) buffers: fgp_fit(X, y) + fgp_predict_mean_var(Xq) with
+                  the H2D of X, y, Xq and the D2H of mean/var inside the timed region
+ * roofline       dominant kernel = gemm_nt_kernel (SYRK/GEMM/TRSM tiles on the fp64 tensor pipe, DMMA): algorithmic
+                  flops of its launches / their summed CUDA-event durations inside the timed steps
+ * cpu_baseline   the oracle (C restatement of the reference's algorithm, 1 thread like the reference) on a bounded sample
+ * --impl reference   the reference arm: the same oracle timed on the host CPU (the Rust crate cannot be built here)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FP64_PEAK_TFLOPS = 37.07  # measured on this pool's B200: tools/microbench/fp64_peak.cu, profiles/fp64_peak_r01.jsonl
+WORKLOADS = {
+    # name: (n, d, q, kernel tag, description)
+    "metric": (16384, 16, 1024, "SquaredExp", "fit: Gram+Cholesky n=16384 d=16 SquaredExp f64; predict mean+variance q=1024"),
+    "c2": (4096, 8, 1024, "SquaredExp", "fit n=4096 d=8 SquaredExp f64 + predict 1024 queries"),
+    "c4": (32768, 32, 1024, "SquaredExp", "fit n=32768 d=32 SquaredExp f64; predict mean+variance q=1024"),
+}
+
+
+def fit_flops(n, d):
+    return n ** 3 / 3.0 + float(n) * n * d
+
+
+def predict_flops(n, d, q):
+    return float(n) * n * q + 2.0 * n * q * d + 4.0 * n * q  # forward TRSM + cross-covariance + mean/var reductions
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def pinned_array(N, shape, order="F"):
+    count = int(np.prod(shape))
+    ptr = N.lib().fgp_alloc_pinned(count * 8)
+    if not ptr:
+        raise MemoryError("fgp_alloc_pinned failed")
+    buf = (C.c_double * count).from_address(ptr)
+    return np.ndarray(shape, dtype=np.float64, buffer=buf, order=order), ptr
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# oracle timing (cpu_baseline leg and the --impl reference arm)
+
+def oracle_step(O, kdesc, X, y, Xq):
+    gp = O.OracleGaussianProcess(O.ZeroPrior(), kdesc, 0.1, None, X, y)
+    if Xq is not None:
+        gp.predict_mean_variance(Xq)
+    return gp
+
+
+def time_oracle(n, d, q, steps, warmup):
+    from friedrich_b200.synthetic import make_dataset, make_inputs
+    from oracle import oracle as O
+    X, y = make_dataset(0x5EED0001, n, d)
+    Xq = make_inputs(0x5EED0002, q, d) if q else None
+    kdesc = O.KernelDesc.make([O.K_SQUARED_EXP], [math.sqrt(d / 6.0), 1.0])
+    for _ in range(warmup):
+        oracle_step(O, kdesc, X, y, Xq)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle_step(O, kdesc, X, y, Xq)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    flops = fit_flops(n, d) + (2.0 * predict_flops(n, d, q) if q else 0.0)  # the reference does both triangular solves
+    return dt, flops
+
+
+def run_reference(args, rank, world):
+    """The reference arm.  friedrich is a Rust crate and this image has no cargo/rustc, so `oracle/_ref` cannot exist;
+    the arm times the oracle port (the reference's algorithm, single-threaded like the crate) on the host CPU."""
+    if rank != 0:
+        return
+    n, d, q, _, desc = WORKLOADS[args.workload]
+    ns, qs = 2048, 256  # bounded sample of the workload: ~1 s per step
+    dt, flops = time_oracle(ns, d, qs, args.steps, args.warmup)
+    val = flops / dt * 1e-12
+    line = {
+        "impl": "reference", "metric": "gp_fit_tflops", "value": val, "unit": "TFLOP/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "n": n, "d": d, "q": q},
+        "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": 1, "kind": "port",
+                         "sample": f"oracle fit n={ns} d={d} + predict_mean_variance q={qs} per step "
+                                   f"(flop rate; the full n={n} fit would take ~{(n / ns) ** 3 * dt / 60:.0f} min)"},
+        "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "host_cores": os.cpu_count(),
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+
+def run_ours(args, rank, local_rank, world):
+    from friedrich_b200 import _native as N
+    from friedrich_b200.kernels import SquaredExp
+    from friedrich_b200.synthetic import make_dataset, make_inputs
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n, d, q, _, desc = WORKLOADS[args.workload]
+    lib = N.lib()
+    h = N.Handle(local_rank)
+    Xs, ys = make_dataset(0x5EED0001 + rank, n, d)
+    Xqs = make_inputs(0x5EED0002 + rank, q, d)
+    X, pX = pinned_array(N, (n, d))
+    y, py = pinned_array(N, (n,))
+    Xq, pq = pinned_array(N, (q, d))
+    X[...], y[...], Xq[...] = Xs, ys, Xqs
+    mean, pm = pinned_array(N, (q,))
+    var, pv = pinned_array(N, (q,))
+    kd = SquaredExp(math.sqrt(d / 6.0), 1.0).device_desc()
+    noise = 0.1
+
+    def fit_host():
+        h.check(lib.fgp_fit(h.ptr, N.dptr(X), n, n, d, N.dptr(y), C.byref(kd), noise, 0, 0.0))
+
+    def refit():
+        h.check(lib.fgp_refit(h.ptr, C.byref(kd), noise, 0, 0.0))
+
+    def predict_host():
+        h.check(lib.fgp_predict_mean_var(h.ptr, C.byref(kd), N.dptr(Xq), q, q, N.dptr(mean), N.dptr(var)))
+
+    def predict_staged():
+        h.check(lib.fgp_predict_staged(h.ptr, C.byref(kd), 1, 1))
+
+    def barrier():
+        if dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    lib.fgp_set_profiling(h.ptr, 1)
+    fit_host()  # first touch: allocations, H2D
+    for _ in range(args.warmup):
+        refit()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- timed region 1: K fit steps, inputs resident in HBM (the factor is 8 n^2 bytes >> L2, no flush needed) ----
+    pms, pfl, pcnt = np.zeros(4), np.zeros(4), np.zeros(4, dtype=np.int64)
+    tms, tfl, tcnt = np.zeros(4), np.zeros(4), np.zeros(4, dtype=np.int64)
+    launches = 0
+    barrier()
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        refit()
+        dev_ms += h.last_device_ms()
+        launches += h.last_launch_count()
+        lib.fgp_profile_summary(h.ptr, N.dptr(pms), N.dptr(pfl), pcnt.ctypes.data_as(C.POINTER(C.c_int64)))
+        tms += pms
+        tfl += pfl
+        tcnt += pcnt
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    fit_ms = max_over_ranks(dev_ms / args.steps)
+
+    # ---- predict throughput, queries resident ------------------------------------------------------------------------
+    h.check(lib.fgp_stage_queries(h.ptr, N.dptr(Xq), q, q))
+    for _ in range(args.warmup):
+        predict_staged()
+    pred_ms = 0.0
+    pred_launches = 0
+    for _ in range(args.steps):
+        predict_staged()
+        pred_ms += h.last_device_ms()
+        pred_launches += h.last_launch_count()
+    pred_ms = max_over_ranks(pred_ms / args.steps)
+
+    # ---- timed region 2: end to end through the C-ABI with host buffers -------------------------------------------------
+    for _ in range(max(1, args.warmup // 2)):
+        fit_host()
+        predict_host()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_fit_ms = 0.0
+    for _ in range(args.steps):
+        t1 = time.perf_counter()
+        fit_host()
+        e2e_fit_ms += (time.perf_counter() - t1) * 1e3
+        predict_host()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    clocks = sampler.stop()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    value = world * fit_flops(n, d) / (fit_ms * 1e-3) * 1e-12
+    gemm_tflops = tfl[0] / (tms[0] * 1e-3) * 1e-12 if tms[0] > 0 else None
+    line = {
+        "metric": "gp_fit_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": fit_ms, "higher_is_better": True,
+        "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "n": n, "d": d, "q": q, "noise": noise, "kernel": "SquaredExp(ls=sqrt(d/6), ampl=1)",
+                   "l2": "inputs larger than L2 (factor = %.2f GB)" % (8.0 * n * n / 1e9),
+                   "multi_gpu": "independent replicas" if world > 1 else "single GPU"},
+        "frac_of_fp64_peak": value / (world * FP64_PEAK_TFLOPS),
+        "predict_qps": world * q / (pred_ms * 1e-3), "predict_ms": pred_ms,
+        "wall_ms_per_step": wall_ms / args.steps,
+        "e2e": {"value": world * (fit_flops(n, d) + predict_flops(n, d, q)) / (e2e_ms * 1e-3) * 1e-12, "unit": "TFLOP/s",
+                "ms_per_step": e2e_ms, "fit_ms": e2e_fit_ms / args.steps,
+                "predict_qps": q / max((e2e_ms - e2e_fit_ms / args.steps) * 1e-3, 1e-9),
+                "h2d_bytes_per_step": 8 * (n * d + n + q * d), "d2h_bytes_per_step": 8 * 2 * q,
+                "what": "fgp_fit(host X, y) + fgp_predict_mean_var(host Xq) -> host mean, var"},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "gemm_nt_kernel", "bound": "tensor", "achieved": gemm_tflops, "peak": FP64_PEAK_TFLOPS,
+                     "unit": "TFLOP/s", "frac": (gemm_tflops / FP64_PEAK_TFLOPS) if gemm_tflops else None,
+                     "traffic": None, "launches": int(tcnt[0]), "share_of_step": float(tms[0] / max(dev_ms, 1e-9)),
+                     "peak_source": "fp64 DMMA m8n8k4 register-resident burst measured on this pool "
+                                    "(MEASURED_PEAKS.json has no fp64 figure; nominal 148 SM x 128 flop/clk x 1.965 GHz = 37.2)"},
+        "kernel_ms_per_step": {"gemm_nt": tms[0] / args.steps, "potrf_diag": tms[1] / args.steps,
+                               "gram": tms[2] / args.steps},
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        ns, qs = (4096, 256) if n >= 4096 else (n, min(q, 256))
+        dt, flops = time_oracle(ns, d, qs, 1, 0)
+        line["cpu_baseline"] = {"value": flops / dt * 1e-12, "unit": "TFLOP/s", "cores": 1, "kind": "port",
+                                "host_cores": os.cpu_count(), "seconds": dt,
+                                "sample": f"oracle fit n={ns} d={d} + predict_mean_variance q={qs}, 1 step, 1 thread "
+                                          f"(the reference is single-threaded)"}
+    print(json.dumps(line), flush=True)
+    for p in (pX, py, pq, pm, pv):
+        lib.fgp_free_pinned(p)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="metric", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

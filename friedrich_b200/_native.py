@@ -77,6 +77,8 @@ SIGNATURES = {
     "fgp_download_alpha": (C.c_int, [_h, _dp]),
     "fgp_last_device_ms": (C.c_double, [_h]),
     "fgp_last_launch_count": (_i64, [_h]),
+    "fgp_set_profiling": (C.c_int, [_h, C.c_int]),
+    "fgp_profile_summary": (C.c_int, [_h, _dp, _dp, C.POINTER(_i64)]),
     "fgp_stage_queries": (C.c_int, [_h, _dp, _i64, _i64]),
     "fgp_predict_staged": (C.c_int, [_h, _kd, C.c_int, C.c_int]),
     "fgp_fetch_predictions": (C.c_int, [_h, _dp, _dp]),

@@ -8,11 +8,78 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace fgp {
 
 constexpr int TILE = 128;  // every matrix on the device is padded to a multiple of TILE ("layout")
 
 __host__ __device__ inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Launch context: the stream plus an optional per-kernel-class profiler (CUDA events around each launch on the
+// launching stream; bench.py's roofline figures come from it, include/fgp.h fgp_set_profiling).
+enum ProfClass { PROF_GEMM = 0, PROF_POTRF_DIAG = 1, PROF_PAIR = 2, PROF_OTHER = 3, PROF_NCLASS = 4 };
+
+struct Profiler {
+    struct Rec { int cls; double flops; cudaEvent_t e0, e1; };
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    std::vector<Rec> recs;
+    double ms[PROF_NCLASS] = {0, 0, 0, 0};
+    double flops[PROF_NCLASS] = {0, 0, 0, 0};
+    int64_t count[PROF_NCLASS] = {0, 0, 0, 0};
+    cudaEvent_t get() {
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            pool.push_back(e);
+        }
+        return pool[used++];
+    }
+    void reset() {
+        used = 0;
+        recs.clear();
+        for (int i = 0; i < PROF_NCLASS; ++i) { ms[i] = 0; flops[i] = 0; count[i] = 0; }
+    }
+    // call after the stream has been synchronised
+    void collect() {
+        for (const Rec& r : recs) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) ms[r.cls] += t;
+            flops[r.cls] += r.flops;
+            count[r.cls] += 1;
+        }
+        recs.clear();
+        used = 0;
+    }
+    void destroy() {
+        for (cudaEvent_t e : pool) cudaEventDestroy(e);
+        pool.clear();
+    }
+};
+
+struct LaunchCtx {
+    cudaStream_t st = nullptr;
+    Profiler* prof = nullptr;  // null: no per-launch events
+};
+
+struct ProfScope {
+    const LaunchCtx& ctx;
+    Profiler::Rec rec;
+    ProfScope(const LaunchCtx& c, int cls, double flops) : ctx(c) {
+        if (ctx.prof) {
+            rec = {cls, flops, ctx.prof->get(), ctx.prof->get()};
+            cudaEventRecord(rec.e0, ctx.st);
+        }
+    }
+    ~ProfScope() {
+        if (ctx.prof) {
+            cudaEventRecord(rec.e1, ctx.st);
+            ctx.prof->recs.push_back(rec);
+        }
+    }
+};
 
 // ---------------------------------------------------------------------------------------------------------------
 // DMMA: D(8x8) += A(8x4, row) * B(4x8, col).  Lane l: g = l >> 2, t = l & 3.

@@ -48,6 +48,8 @@ void write_covariance(fgp_model* m, const KernelTraits& kt, const fgp_kernel_des
                       int64_t ld, int64_t valid_rows, int64_t valid_cols, double noise2) {
     const DevKernel dk = to_dev(kd);
     const int mode = (kt.need_d2 ? PAIR_D2 : 0) | (kt.need_dot ? PAIR_DOT : 0);
+    const LaunchCtx lc = m->ctx();
+    ProfScope ps(lc, PROF_PAIR, (double)pa.rows * pa.cols * (pa.symmetric ? 0.5 : 1.0) * 2.0 * pa.dp);
     if (kt.kind == KIND_SQEXP) {
         CovWriteEpi<KIND_SQEXP> e{dk, out, ld, valid_rows, valid_cols, pa.symmetric, noise2};
         launch_cov<KIND_SQEXP, PAIR_D2>(pa, e, m->st);
@@ -102,8 +104,8 @@ int reserve_training(fgp_model* m, int64_t cap_rows, int64_t dp, bool keep) {
     CU(m, m->z.reserve((size_t)cap_rows));
     CU(m, m->alpha.reserve((size_t)cap_rows));
     CU(m, m->work.reserve((size_t)cap_rows));
-    CU(m, m->inv.reserve((size_t)cap_rows * TILE));
-    CU(m, m->invT.reserve((size_t)cap_rows * TILE));
+    CU(m, m->inv.reserve((size_t)cap_rows * TILE, keep, m->st));
+    CU(m, m->invT.reserve((size_t)cap_rows * TILE, keep, m->st));
     return FGP_OK;
 }
 
@@ -113,7 +115,7 @@ int factor_resident(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits&
     CU(m, cudaMemsetAsync(m->info_d, 0, sizeof(int), m->st));
     write_covariance(m, kt, kd, train_pair_args(m), m->L.p, m->cap, m->n, m->n, noise * noise);
     PotrfCounters cnt;
-    potrf_lower(m->L.p, m->cap, m->np, 0, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->st, &cnt);
+    potrf_lower(m->L.p, m->cap, m->np, 0, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->ctx(), &cnt);
     m->launches += cnt.launches;
     CU(m, cudaMemcpyAsync(m->info_h, m->info_d, sizeof(int), cudaMemcpyDeviceToHost, m->st));
     solve_alpha(m);
@@ -194,7 +196,7 @@ int predict_device(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& 
         m->have_mean = true;
     }
     if (want_var) {
-        m->launches += trsm_fwd_t(m->bt.p, qp, qp, m->L.p, m->cap, m->inv.p, 0, np / TILE, nullptr, m->st);
+        m->launches += trsm_fwd_t(m->bt.p, qp, qp, m->L.p, m->cap, m->inv.p, 0, np / TILE, nullptr, m->ctx());
         rowreduce_partial_kernel<1><<<rgrid, 128, 0, m->st>>>(m->bt.p, qp, nullptr, m->partial.p, qp);
         rowreduce_final_kernel<<<(unsigned)(qp / 128), 128, 0, m->st>>>(m->partial.p, chunks, qp, m->q, 1, dk, m->qnr.p,
                                                                          m->var_d.p);
@@ -283,6 +285,7 @@ FGP_EXPORT int fgp_destroy(fgp_model* m) {
         if (m->ev1) cudaEventDestroy(m->ev1);
         if (m->evA) cudaEventDestroy(m->evA);
         if (m->evB) cudaEventDestroy(m->evB);
+        m->prof.destroy();
         if (m->st) cudaStreamDestroy(m->st);
         if (m->st2) cudaStreamDestroy(m->st2);
     }
@@ -296,6 +299,23 @@ FGP_EXPORT int64_t fgp_num_samples(const fgp_model* m) { return m ? m->n : 0; }
 FGP_EXPORT int64_t fgp_num_dims(const fgp_model* m) { return m ? m->d : 0; }
 FGP_EXPORT double fgp_last_device_ms(const fgp_model* m) { return m ? (double)m->last_ms : 0.0; }
 FGP_EXPORT int64_t fgp_last_launch_count(const fgp_model* m) { return m ? m->launches : 0; }
+
+FGP_EXPORT int fgp_set_profiling(fgp_model* m, int on) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    m->profiling = on != 0;
+    m->prof.reset();
+    return FGP_OK;
+}
+FGP_EXPORT int fgp_profile_summary(const fgp_model* m, double* ms, double* flops, int64_t* count) {
+    if (!m || !ms || !flops || !count) return FGP_ERR_BAD_ARG;
+    for (int i = 0; i < PROF_NCLASS; ++i) {
+        ms[i] = m->prof.ms[i];
+        flops[i] = m->prof.flops[i];
+        count[i] = m->prof.count[i];
+    }
+    return FGP_OK;
+}
 
 FGP_EXPORT void* fgp_alloc_pinned(size_t bytes) {
     void* p = nullptr;
@@ -461,7 +481,7 @@ FGP_EXPORT int fgp_predict_cov(fgp_model* m, const fgp_kernel_desc* kernel, cons
     g.B = m->bt.p; g.ldb = qp;
     g.M = g.N = (int)qp; g.K = (int)m->np;
     g.alpha = -1.0; g.beta_one = 1; g.lower = 0; g.k_from_tile = 0;
-    m->launches += gemm_nt_launch(g, m->st) > 0;
+    m->launches += gemm_nt_launch(g, m->ctx()) > 0;
     FGP_TRY(end_timed(m));
     // q x q result straight into the caller's buffer
     CU(m, cudaMemcpy2DAsync(cov, ldc * sizeof(double), m->kqq.p, qp * sizeof(double), q * sizeof(double), q,
@@ -597,9 +617,9 @@ FGP_EXPORT int fgp_add_samples(fgp_model* m, const double* Xnew, int64_t ldx, in
     // rows [jb*128, np_new) x columns [0, jb*128):  A <- A * L11^-T, and the trailing block gets -= A A^T
     double* Arows = m->L.p + jb * TILE;  // row offset inside every column
     m->launches += trsm_fwd_t(Arows, m->cap, np_new - jb * TILE, m->L.p, m->cap, m->inv.p, 0, jb, Arows + jb * TILE * m->cap,
-                              m->st);
+                              m->ctx());
     PotrfCounters cnt;
-    potrf_lower(m->L.p, m->cap, np_new, jb, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->st, &cnt);
+    potrf_lower(m->L.p, m->cap, np_new, jb, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->ctx(), &cnt);
     m->launches += cnt.launches;
     CU(m, cudaMemcpyAsync(m->info_h, m->info_d, sizeof(int), cudaMemcpyDeviceToHost, m->st));
     solve_alpha(m);
@@ -637,7 +657,7 @@ FGP_EXPORT int fgp_cholesky_lower(int device, double* A, int64_t lda, int64_t n,
         set_identity_kernel<<<(unsigned)((np + 255) / 256), 256>>>(dA, np, np);  // padding block = I
         cudaMemcpy2DAsync(dA, (size_t)np * 8, A, (size_t)lda * 8, (size_t)n * 8, n, cudaMemcpyHostToDevice, 0);
         PotrfCounters cnt;
-        potrf_lower(dA, np, np, 0, dinv, dinv + np * TILE, 0, 0.0, dinfo, 0, &cnt);
+        potrf_lower(dA, np, np, 0, dinv, dinv + np * TILE, 0, 0.0, dinfo, LaunchCtx{}, &cnt);
         cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, 0);
         cudaMemcpy2DAsync(A, (size_t)lda * 8, dA, (size_t)np * 8, (size_t)n * 8, n, cudaMemcpyDeviceToHost, 0);
         if (cudaStreamSynchronize(0) != cudaSuccess) rc = FGP_ERR_CUDA;
@@ -676,7 +696,7 @@ FGP_EXPORT int fgp_dbg_gemm_nt(int device, double* C, int64_t ldc, const double*
         g.B = dB; g.ldb = N;
         g.M = M; g.N = N; g.K = K;
         g.alpha = alpha; g.beta_one = beta_one; g.lower = lower; g.k_from_tile = 0;
-        gemm_nt_launch(g, 0);
+        gemm_nt_launch(g, LaunchCtx{});
         if (cudaDeviceSynchronize() != cudaSuccess) rc = FGP_ERR_CUDA;
         cudaMemcpy2D(C, (size_t)ldc * 8, dC, (size_t)M * 8, (size_t)M * 8, N, cudaMemcpyDeviceToHost);
     }

@@ -156,13 +156,26 @@ inline cudaError_t gemm_nt_prepare() {
     return e;
 }
 
+// algorithmic flops of one launch (what the roofline figure in bench.py is computed from)
+inline double gemm_nt_flops(const GemmArgs& g) {
+    const double tm = g.M / GEMM_BM, tn = g.N / GEMM_BN;
+    if (g.k_from_tile) {  // U U^T on upper-triangular operands: tile (i, j<=i) contracts over K - 128 i
+        double f = 0.0;
+        for (int i = 0; i < (int)tm; ++i) f += (double)(i + 1) * (g.K - GEMM_BM * i);
+        return 2.0 * GEMM_BM * GEMM_BN * f;
+    }
+    const double tiles = g.lower ? tm * (tm + 1) / 2 : tm * tn;
+    return 2.0 * GEMM_BM * GEMM_BN * tiles * g.K;
+}
+
 // launches nothing when the problem is empty; returns the number of tiles launched
-inline int64_t gemm_nt_launch(const GemmArgs& g, cudaStream_t stream) {
+inline int64_t gemm_nt_launch(const GemmArgs& g, const LaunchCtx& ctx) {
     if (g.M <= 0 || g.N <= 0) return 0;
     const int64_t tm = g.M / GEMM_BM, tn = g.N / GEMM_BN;
     const int64_t tiles = g.lower ? tm * (tm + 1) / 2 : tm * tn;
     if (g.K <= 0) return 0;
-    gemm_nt_kernel<<<(unsigned)tiles, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(g);
+    ProfScope ps(ctx, PROF_GEMM, gemm_nt_flops(g));
+    gemm_nt_kernel<<<(unsigned)tiles, GEMM_THREADS, GEMM_SMEM_BYTES, ctx.st>>>(g);
     return tiles;
 }
 

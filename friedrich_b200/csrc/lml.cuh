@@ -118,7 +118,7 @@ inline int lml_gradient_device(fgp_model* m, const fgp_kernel_desc* kd, const Ke
     CU(m, cudaMemsetAsync(m->U.p, 0, (size_t)np * np * sizeof(double), m->st));
     set_identity_kernel<<<(unsigned)((np + 255) / 256), 256, 0, m->st>>>(m->U.p, np, np);
     m->launches += 1;
-    m->launches += trsm_fwd_t(m->U.p, np, np, m->L.p, m->cap, m->inv.p, 0, nb, nullptr, m->st, true);
+    m->launches += trsm_fwd_t(m->U.p, np, np, m->L.p, m->cap, m->inv.p, 0, nb, nullptr, m->ctx(), true);
     // K^-1 = U U^T, lower triangle
     {
         GemmArgs g{};
@@ -127,7 +127,7 @@ inline int lml_gradient_device(fgp_model* m, const fgp_kernel_desc* kd, const Ke
         g.B = m->U.p; g.ldb = np;
         g.M = g.N = (int)np; g.K = (int)np;
         g.alpha = 1.0; g.beta_one = 0; g.lower = 1; g.k_from_tile = 1;
-        m->launches += gemm_nt_launch(g, m->st) > 0;
+        m->launches += gemm_nt_launch(g, m->ctx()) > 0;
     }
     // fused gradient reductions
     PairArgs pa{};

@@ -82,6 +82,9 @@ struct fgp_model {
     // measurement ---------------------------------------------------------------------------------------------
     float last_ms = 0.f;
     int64_t launches = 0;
+    bool profiling = false;
+    fgp::Profiler prof;
+    fgp::LaunchCtx ctx() { return fgp::LaunchCtx{st, profiling ? &prof : nullptr}; }
 };
 
 namespace fgp {
@@ -126,12 +129,14 @@ inline int ensure_pinned(fgp_model* m, size_t doubles) {
 
 inline void begin_timed(fgp_model* m) {
     m->launches = 0;
+    if (m->profiling) m->prof.reset();
     cudaEventRecord(m->ev0, m->st);
 }
 inline int end_timed(fgp_model* m) {
     CU(m, cudaEventRecord(m->ev1, m->st));
     CU(m, cudaEventSynchronize(m->ev1));
     CU(m, cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
+    if (m->profiling) m->prof.collect();
     CU(m, cudaGetLastError());
     return FGP_OK;
 }

@@ -190,7 +190,7 @@ struct PotrfCounters {
 // jb_begin must already hold final factor values in ALL rows (used by add_samples: the caller has applied them to
 // the trailing block). invdiag / invdiagT: [np/128][128*128] (inverse blocks and their transposes). info: device int, 0 on entry.
 inline void potrf_lower(double* A, int64_t lda, int64_t np, int64_t jb_begin, double* invdiag, double* invdiagT, int has_sub,
-                        double sub, int* info, cudaStream_t st, PotrfCounters* cnt) {
+                        double sub, int* info, const LaunchCtx& st, PotrfCounters* cnt) {
     const int64_t nb = np / TILE;
     for (int64_t J = jb_begin; J < nb; J += PANEL_TILES) {
         const int64_t Jend = (J + PANEL_TILES < nb) ? J + PANEL_TILES : nb;
@@ -205,8 +205,12 @@ inline void potrf_lower(double* A, int64_t lda, int64_t np, int64_t jb_begin, do
                 g.alpha = -1.0; g.beta_one = 1; g.lower = 0; g.k_from_tile = 0;
                 cnt->launches += gemm_nt_launch(g, st) > 0;
             }
-            potrf_diag_kernel<<<1, 256, DIAG_SMEM_BYTES, st>>>(Ajj, lda, invdiag + j * TILE * TILE, invdiagT + j * TILE * TILE,
-                                                               has_sub, sub, info, (int)(j * TILE));
+            {
+                ProfScope ps(st, PROF_POTRF_DIAG, 128.0 * 128.0 * 128.0 / 3.0);
+                potrf_diag_kernel<<<1, 256, DIAG_SMEM_BYTES, st.st>>>(Ajj, lda, invdiag + j * TILE * TILE,
+                                                                      invdiagT + j * TILE * TILE, has_sub, sub, info,
+                                                                      (int)(j * TILE));
+            }
             cnt->launches += 1;
             if (j + 1 < nb) {
                 GemmArgs g{};

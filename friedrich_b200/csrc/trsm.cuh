@@ -20,7 +20,7 @@ namespace fgp {
 
 // returns the number of kernel launches
 inline int64_t trsm_fwd_t(double* Xt, int64_t ldx, int64_t M, const double* L, int64_t ldl, const double* inv,
-                          int64_t i_begin, int64_t i_end, double* trailing, cudaStream_t st, bool tri_rows = false) {
+                          int64_t i_begin, int64_t i_end, double* trailing, const LaunchCtx& st, bool tri_rows = false) {
     int64_t launches = 0;
     for (int64_t i = i_begin; i < i_end; ++i) {
         const int64_t Mi = tri_rows ? std::min<int64_t>(M, (i + 1) * TILE) : M;

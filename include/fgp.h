@@ -116,6 +116,11 @@ int fgp_cholesky_lower(int device, double* A, int64_t lda, int64_t n, int64_t* f
  * Device time (CUDA events on the model's stream) and number of kernel launches of the last entry-point call. */
 double fgp_last_device_ms(const fgp_model* m);
 int64_t fgp_last_launch_count(const fgp_model* m);
+/* Per-kernel-class device timing of the last entry-point call (CUDA events around every launch on the model's stream).
+ * Classes: 0 = gemm_nt (SYRK / GEMM / TRSM-as-GEMM, fp64 tensor pipe), 1 = potrf_diag, 2 = pair tiles (Gram,
+ * cross-covariance, gradient reductions), 3 = other.  ms / flops / count are arrays of 4. */
+int fgp_set_profiling(fgp_model* m, int on);
+int fgp_profile_summary(const fgp_model* m, double* ms, double* flops, int64_t* count);
 /* Resident-input predict for kernel-only timing: stage queries once, then run the device part repeatedly. */
 int fgp_stage_queries(fgp_model* m, const double* Xq, int64_t ldq, int64_t q);
 int fgp_predict_staged(fgp_model* m, const fgp_kernel_desc* kernel, int want_mean, int want_var);

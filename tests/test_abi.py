@@ -1,0 +1,73 @@
+"""CPU: the C-ABI shared library builds, loads and exports exactly the symbols include/fgp.h declares, and the ctypes
+binding (the stand-in for the Rust `extern "C"` block) names the same set.  No compute call is made here."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "fgp.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fgp_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from friedrich_b200 import build
+    return build.build()
+
+
+def test_header_declares_the_reference_seam():
+    syms = _header_symbols()
+    for s in ("fgp_fit", "fgp_refit", "fgp_add_samples", "fgp_predict_mean", "fgp_predict_var", "fgp_predict_mean_var",
+              "fgp_predict_cov", "fgp_likelihood", "fgp_lml_gradient", "fgp_mean_pair_distance", "fgp_download_factor"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", built_lib], text=True)
+    exported = set(re.findall(r"\bT (fgp_[a-z0-9_]+)", out))
+    missing = [s for s in _header_symbols() if s not in exported]
+    assert not missing, f"declared in include/fgp.h but not exported: {missing}"
+    # nothing but the C-ABI leaks out of the library
+    leaked = [l.split()[-1] for l in out.splitlines() if " T " in l and not l.split()[-1].startswith("fgp_")]
+    assert not leaked, leaked
+
+
+def test_ctypes_binding_matches_header(built_lib):
+    from friedrich_b200 import _native as N
+    assert sorted(N.SIGNATURES) == _header_symbols()
+    lib = N.lib()  # resolves every symbol or raises
+    assert b"sm_100a" in lib.fgp_version()
+
+
+def test_no_cpu_fallback_without_device(built_lib):
+    """Without a CUDA device fgp_create must fail loudly (this container has no GPU)."""
+    import ctypes as C
+    from friedrich_b200 import _native as N
+    probe = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True) if os.path.exists("/usr/bin/nvidia-smi") else None
+    if probe is not None and probe.returncode == 0 and "GPU" in probe.stdout:
+        pytest.skip("a GPU is present")
+    with pytest.raises(N.FgpError):
+        N.Handle(0)
+    h = C.c_void_p()
+    assert N.lib().fgp_create(0, C.byref(h)) == N.FGP_ERR_CUDA
+    assert not h.value
+
+
+def test_library_does_not_link_blas_or_torch(built_lib):
+    out = subprocess.check_output(["ldd", built_lib], text=True)
+    for banned in ("cublas", "cusolver", "torch", "oracle"):
+        assert banned not in out.lower(), out
+
+
+def test_kernel_desc_layout_matches_header():
+    import ctypes as C
+    from friedrich_b200 import _native as N
+    from oracle import oracle as O
+    assert C.sizeof(N.KernelDesc) == 4 + 4 * 15 + 8 * 24 == C.sizeof(O.KernelDesc)
+    assert N.KernelDesc.param.offset == 64
