@@ -152,7 +152,9 @@ def test_fit_predict_parity(n, d, q, kname):
     mr, vr = ref.predict_mean_variance(Xq)
     assert close(m, mr) and close(v, vr)
     assert abs(gp.likelihood() - ref.likelihood()) < 1e-9 * abs(ref.likelihood())
-    qs = min(q, 64)
+    # d=1: the posterior covariance of many queries on a line is numerically singular (the reference's
+    # MultivariateNormal::new would panic as well), so sample only a handful there
+    qs = min(q, 64) if d > 1 else 5
     assert np.allclose(gp.predict_covariance(Xq[:qs]), ref.predict_covariance(Xq[:qs]), rtol=1e-8, atol=1e-11)
     mvn = gp.sample_at(Xq[:qs])
     mean2, cov2 = ref.sample_at_params(Xq[:qs])
