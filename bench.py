@@ -211,6 +211,8 @@ def run_ours(args, rank, local_rank, world):
         return float(t.item())
 
     lib.fgp_set_profiling(h.ptr, 1)
+    if args.no_lookahead:
+        lib.fgp_set_option(h.ptr, N.FGP_OPT_LOOKAHEAD, 0)
     fit_host()  # first touch: allocations, H2D
     for _ in range(args.warmup):
         refit()
@@ -318,6 +320,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="metric", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lookahead", action="store_true", help="A/B: single-stream Cholesky schedule")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

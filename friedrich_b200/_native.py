@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libfgp_sm100.so")
 MAX_OPS = 15
 MAX_PARAMS = 24
 
+FGP_OPT_LOOKAHEAD = 1
 FGP_OK, FGP_ERR_NOT_POSDEF, FGP_ERR_BAD_ARG, FGP_ERR_BAD_KERNEL, FGP_ERR_CUDA, FGP_ERR_NOT_FITTED, FGP_ERR_COMM = range(7)
 
 
@@ -78,6 +79,7 @@ SIGNATURES = {
     "fgp_last_device_ms": (C.c_double, [_h]),
     "fgp_last_launch_count": (_i64, [_h]),
     "fgp_set_profiling": (C.c_int, [_h, C.c_int]),
+    "fgp_set_option": (C.c_int, [_h, C.c_int, _i64]),
     "fgp_profile_summary": (C.c_int, [_h, _dp, _dp, C.POINTER(_i64)]),
     "fgp_stage_queries": (C.c_int, [_h, _dp, _i64, _i64]),
     "fgp_predict_staged": (C.c_int, [_h, _kd, C.c_int, C.c_int]),

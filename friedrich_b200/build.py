@@ -1,18 +1,22 @@
-"""In-tree build of libfgp_sm100.so: plain `nvcc -shared` of the .cu sources for sm_100a (no PyTorch, no cuBLAS /
-cuSOLVER; the only libraries linked are the CUDA runtime and — for the multi-GPU path — NCCL)."""
+"""In-tree build of libfgp_sm100.so: plain `nvcc` of the .cu sources for sm_100a (no PyTorch, no cuBLAS / cuSOLVER; the
+only libraries linked are the CUDA runtime and — for the multi-GPU path — NCCL).  Each .cu is its own translation unit
+(no relocatable device code: kernels are only launched from the TU that defines them); the TUs compile in parallel."""
 from __future__ import annotations
 
 import glob
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
+OBJ = os.path.join(CSRC, "obj")
 LIB = os.path.join(_HERE, "libfgp_sm100.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared"]
+              "-Xcompiler", "-fPIC,-fvisibility=hidden"]
+LINK_LIBS = ["-lnccl"]
 
 
 def _nvcc():
@@ -26,21 +30,42 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
-def needs_build():
-    if not os.path.exists(LIB):
+def _headers():
+    return glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(_HERE, "..", "include", "*.h"))
+
+
+def _obj(src):
+    return os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB)
-    deps = glob.glob(os.path.join(CSRC, "*")) + glob.glob(os.path.join(_HERE, "..", "include", "*.h"))
+    t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def needs_build():
+    return _stale(LIB, sources() + _headers())
+
+
 def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + sources()
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    subprocess.check_call(cmd)
+    os.makedirs(OBJ, exist_ok=True)
+    hdrs = _headers()
+    todo = [s for s in sources() if force or _stale(_obj(s), [s] + hdrs)]
+
+    def compile_one(src):
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", "-o", _obj(src), src]
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+        subprocess.check_call(cmd)
+
+    if todo:
+        with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 4)) as ex:
+            list(ex.map(compile_one, todo))
+    objs = [_obj(s) for s in sources()]
+    if force or todo or _stale(LIB, objs):
+        subprocess.check_call([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + LINK_LIBS)
     return LIB
 
 

@@ -125,6 +125,11 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                  : "memory");
 }
 
+// asynchronous L2 prefetch of `bytes` (multiple of 16) starting at a 16-byte aligned global address
+__device__ __forceinline__ void l2_prefetch(const void* gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem), "r"(bytes) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -23,6 +23,7 @@
 #include "vector_kernels.cuh"
 #include "trsm.cuh"
 #include "lml.cuh"
+#include "covariance.cuh"
 
 using namespace fgp;
 
@@ -36,33 +37,6 @@ int upload_colmajor(fgp_model* m, const double* src, int64_t ld, int64_t rows, i
     CU(m, cudaMemcpy2DAsync(m->staging.p, rows * sizeof(double), src, ld * sizeof(double), rows * sizeof(double), cols,
                             cudaMemcpyHostToDevice, m->st));
     return FGP_OK;
-}
-
-// ---- Gram / cross-covariance launch -----------------------------------------------------------------------------
-template <int KIND, int MODE>
-void launch_cov(const PairArgs& pa, const CovWriteEpi<KIND>& epi, cudaStream_t st) {
-    pair_tile_kernel<MODE, CovWriteEpi<KIND>><<<pair_grid(pa), 256, 0, st>>>(pa, epi);
-}
-
-void write_covariance(fgp_model* m, const KernelTraits& kt, const fgp_kernel_desc* kd, const PairArgs& pa, double* out,
-                      int64_t ld, int64_t valid_rows, int64_t valid_cols, double noise2) {
-    const DevKernel dk = to_dev(kd);
-    const int mode = (kt.need_d2 ? PAIR_D2 : 0) | (kt.need_dot ? PAIR_DOT : 0);
-    const LaunchCtx lc = m->ctx();
-    ProfScope ps(lc, PROF_PAIR, (double)pa.rows * pa.cols * (pa.symmetric ? 0.5 : 1.0) * 2.0 * pa.dp);
-    if (kt.kind == KIND_SQEXP) {
-        CovWriteEpi<KIND_SQEXP> e{dk, out, ld, valid_rows, valid_cols, pa.symmetric, noise2};
-        launch_cov<KIND_SQEXP, PAIR_D2>(pa, e, m->st);
-    } else if (kt.kind == KIND_MATERN2) {
-        CovWriteEpi<KIND_MATERN2> e{dk, out, ld, valid_rows, valid_cols, pa.symmetric, noise2};
-        launch_cov<KIND_MATERN2, PAIR_D2>(pa, e, m->st);
-    } else {
-        CovWriteEpi<KIND_GENERIC> e{dk, out, ld, valid_rows, valid_cols, pa.symmetric, noise2};
-        if (mode == PAIR_D2) launch_cov<KIND_GENERIC, PAIR_D2>(pa, e, m->st);
-        else if (mode == PAIR_DOT) launch_cov<KIND_GENERIC, PAIR_DOT>(pa, e, m->st);
-        else launch_cov<KIND_GENERIC, PAIR_BOTH>(pa, e, m->st);
-    }
-    m->launches += 1;
 }
 
 PairArgs train_pair_args(const fgp_model* m) {
@@ -82,12 +56,12 @@ void solve_alpha(fgp_model* m) {
     const int nb = (int)(m->np / TILE);
     cudaMemcpyAsync(m->work.p, m->y.p, m->np * sizeof(double), cudaMemcpyDeviceToDevice, m->st);
     for (int j = 0; j < nb; ++j) {
-        trsv_fwd_kernel<<<nb - j, 128, 0, m->st>>>(m->L.p, m->cap, m->inv.p, m->work.p, m->z.p, j);
+        trsv_fwd_kernel<<<nb - j, TRSV_THREADS, 0, m->st>>>(m->L.p, m->cap, m->inv.p, m->work.p, m->z.p, j);
         m->launches += 1;
     }
     cudaMemcpyAsync(m->work.p, m->z.p, m->np * sizeof(double), cudaMemcpyDeviceToDevice, m->st);
     for (int j = nb - 1; j >= 0; --j) {
-        trsv_adj_kernel<<<j + 1, 128, 0, m->st>>>(m->L.p, m->cap, m->invT.p, m->work.p, m->alpha.p, j, nb);
+        trsv_adj_kernel<<<j + 1, TRSV_THREADS, 0, m->st>>>(m->L.p, m->cap, m->invT.p, m->work.p, m->alpha.p, j, nb);
         m->launches += 1;
     }
 }
@@ -115,7 +89,9 @@ int factor_resident(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits&
     CU(m, cudaMemsetAsync(m->info_d, 0, sizeof(int), m->st));
     write_covariance(m, kt, kd, train_pair_args(m), m->L.p, m->cap, m->n, m->n, noise * noise);
     PotrfCounters cnt;
-    potrf_lower(m->L.p, m->cap, m->np, 0, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->ctx(), &cnt);
+    const PotrfLookahead la{m->st2, m->evA, m->evB};
+    potrf_lower(m->L.p, m->cap, m->np, 0, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->ctx(), m->lookahead ? &la : nullptr,
+                &cnt);
     m->launches += cnt.launches;
     CU(m, cudaMemcpyAsync(m->info_h, m->info_d, sizeof(int), cudaMemcpyDeviceToHost, m->st));
     solve_alpha(m);
@@ -252,8 +228,10 @@ FGP_EXPORT int fgp_create(int device, fgp_model** out) {
     if (!m) return FGP_ERR_CUDA;
     m->device = device;
     DeviceGuard dg(device);
-    bool ok = cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&m->st2, cudaStreamNonBlocking) == cudaSuccess &&
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // st2 = panel stream of the look-ahead Cholesky: highest priority
+    bool ok = cudaStreamCreateWithPriority(&m->st, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&m->st2, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
               cudaEventCreate(&m->ev0) == cudaSuccess && cudaEventCreate(&m->ev1) == cudaSuccess &&
               cudaEventCreateWithFlags(&m->evA, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&m->evB, cudaEventDisableTiming) == cudaSuccess &&
@@ -306,6 +284,14 @@ FGP_EXPORT int fgp_set_profiling(fgp_model* m, int on) {
     m->profiling = on != 0;
     m->prof.reset();
     return FGP_OK;
+}
+FGP_EXPORT int fgp_set_option(fgp_model* m, int option, int64_t value) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    switch (option) {
+        case FGP_OPT_LOOKAHEAD: m->lookahead = value != 0; return FGP_OK;
+        default: return fail(m, FGP_ERR_BAD_ARG, "unknown option");
+    }
 }
 FGP_EXPORT int fgp_profile_summary(const fgp_model* m, double* ms, double* flops, int64_t* count) {
     if (!m || !ms || !flops || !count) return FGP_ERR_BAD_ARG;
@@ -619,7 +605,9 @@ FGP_EXPORT int fgp_add_samples(fgp_model* m, const double* Xnew, int64_t ldx, in
     m->launches += trsm_fwd_t(Arows, m->cap, np_new - jb * TILE, m->L.p, m->cap, m->inv.p, 0, jb, Arows + jb * TILE * m->cap,
                               m->ctx());
     PotrfCounters cnt;
-    potrf_lower(m->L.p, m->cap, np_new, jb, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->ctx(), &cnt);
+    const PotrfLookahead la{m->st2, m->evA, m->evB};
+    potrf_lower(m->L.p, m->cap, np_new, jb, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->ctx(), m->lookahead ? &la : nullptr,
+                &cnt);
     m->launches += cnt.launches;
     CU(m, cudaMemcpyAsync(m->info_h, m->info_d, sizeof(int), cudaMemcpyDeviceToHost, m->st));
     solve_alpha(m);
@@ -654,10 +642,10 @@ FGP_EXPORT int fgp_cholesky_lower(int device, double* A, int64_t lda, int64_t n,
     if (rc == FGP_OK) {
         cudaMemsetAsync(dA, 0, (size_t)np * np * 8, 0);
         cudaMemsetAsync(dinfo, 0, sizeof(int), 0);
-        set_identity_kernel<<<(unsigned)((np + 255) / 256), 256>>>(dA, np, np);  // padding block = I
+        launch_set_identity(dA, np, np, 0);  // padding block = I
         cudaMemcpy2DAsync(dA, (size_t)np * 8, A, (size_t)lda * 8, (size_t)n * 8, n, cudaMemcpyHostToDevice, 0);
         PotrfCounters cnt;
-        potrf_lower(dA, np, np, 0, dinv, dinv + np * TILE, 0, 0.0, dinfo, LaunchCtx{}, &cnt);
+        potrf_lower(dA, np, np, 0, dinv, dinv + np * TILE, 0, 0.0, dinfo, LaunchCtx{}, nullptr, &cnt);
         cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, 0);
         cudaMemcpy2DAsync(A, (size_t)lda * 8, dA, (size_t)np * 8, (size_t)n * 8, n, cudaMemcpyDeviceToHost, 0);
         if (cudaStreamSynchronize(0) != cudaSuccess) rc = FGP_ERR_CUDA;

@@ -83,6 +83,7 @@ struct fgp_model {
     float last_ms = 0.f;
     int64_t launches = 0;
     bool profiling = false;
+    bool lookahead = true;                 // two-stream panel look-ahead in the blocked Cholesky (fgp_set_option)
     fgp::Profiler prof;
     fgp::LaunchCtx ctx() { return fgp::LaunchCtx{st, profiling ? &prof : nullptr}; }
 };

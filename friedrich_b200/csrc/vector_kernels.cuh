@@ -11,7 +11,7 @@
 namespace fgp {
 
 // mu[k] = mean_i src[i + k*ld], i < n.  One block per column, deterministic tree.
-__global__ void __launch_bounds__(256) col_mean_kernel(const double* __restrict__ src, int64_t ld, int64_t n, double* mu) {
+static __global__ void __launch_bounds__(256) col_mean_kernel(const double* __restrict__ src, int64_t ld, int64_t n, double* mu) {
     __shared__ double red[256];
     const int k = blockIdx.x;
     double s = 0.0;
@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256) col_mean_kernel(const double* __restrict_
 
 // src: n x d column-major (ld). Writes rows [row0, row0 + rows_total) of the row-major [.][dp] arrays:
 // raw, centred (raw - mu for k < d), and the squared norms of both; rows >= row0 + n and columns >= d are zero.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 convert_points_kernel(const double* __restrict__ src, int64_t ld, int64_t n, int d, int dp, const double* __restrict__ mu,
                       int64_t row0, int64_t rows_total, double* xr, double* xc, double* nrm_c, double* nrm_r) {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -51,80 +51,101 @@ convert_points_kernel(const double* __restrict__ src, int64_t ld, int64_t n, int
 }
 
 // ---- blocked single-RHS solves with the inverted diagonal blocks ------------------------------------------------
+// Both sweeps are HBM-bound (they read L once: 8 n^2/2 bytes) but latency-critical: nb dependent block steps.  Every
+// CTA therefore issues ALL its loads of a 128x128 tile up front (512 threads x 32 independent 8-byte loads), reduces
+// through shared memory in a fixed order (deterministic), and the step count is one launch per block.
+constexpr int TRSV_THREADS = 512;
+
+// y[r] = sum_c M[r + c*ldm] * xs[c], r < 128, c < 128; thread (r = tid & 127, quarter = tid >> 7) sums 32 columns with 4
+// interleaved accumulators, the quarters are added in order.  Result valid in threads with tid < 128.
+__device__ __forceinline__ double tile_matvec_512(const double* __restrict__ M, int64_t ldm, const double* xs, double* red) {
+    const int r = threadIdx.x & 127, h = threadIdx.x >> 7;
+    const double* p = M + r + (int64_t)(32 * h) * ldm;
+    double v[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] = __ldcg(p + (int64_t)c * ldm);
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+        a0 = fma(v[c], xs[32 * h + c], a0);
+        a1 = fma(v[c + 1], xs[32 * h + c + 1], a1);
+        a2 = fma(v[c + 2], xs[32 * h + c + 2], a2);
+        a3 = fma(v[c + 3], xs[32 * h + c + 3], a3);
+    }
+    red[h * 128 + r] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    double out = 0.0;
+    if (threadIdx.x < 128) out = (red[r] + red[128 + r]) + (red[256 + r] + red[384 + r]);
+    __syncthreads();
+    return out;
+}
+
 // Forward (L x = b), right-looking over 128-blocks. Launch j = 0 .. nb-1 with grid = nb - j:
-//   block 0 solves x_j = inv_j * b_j (b_j is final: every earlier launch has been applied to it);
-//   block t > 0 waits for nothing: it applies the PREVIOUS solution, b_R -= L[R, j-1] x_{j-1}, R = j + t ... so the
-// kernel is split in two phases per launch: (1) every block R = j + blockIdx.x applies x_{j-1} (when j > 0),
-// (2) block 0 solves x_j.
-__global__ void __launch_bounds__(128)
+//   (1) every block R = j + blockIdx.x applies the PREVIOUS solution (when j > 0): b_R -= L[R, j-1] x_{j-1};
+//   (2) block 0 then solves x_j = inv_j * b_j (b_j is final at that point).
+static __global__ void __launch_bounds__(TRSV_THREADS)
 trsv_fwd_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ inv, double* b, double* x, int j) {
     __shared__ double xs[128];
-    const int r = threadIdx.x;
+    __shared__ double red[512];
+    const int r = threadIdx.x & 127;
     const int R = j + blockIdx.x;
-    const int64_t row = (int64_t)R * 128 + r;
-    double v = b[row];
+    const int64_t row0 = (int64_t)R * 128;
+    double v = 0.0;
+    if (threadIdx.x < 128) v = b[row0 + r];
     if (j > 0) {
-        xs[r] = x[(int64_t)(j - 1) * 128 + r];
+        if (threadIdx.x < 128) xs[r] = x[(int64_t)(j - 1) * 128 + r];
         __syncthreads();
-        const double* Lp = L + row + (int64_t)(j - 1) * 128 * ld;
-        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        for (int c = 0; c < 128; c += 4) {
-            a0 = fma(Lp[(int64_t)c * ld], xs[c], a0);
-            a1 = fma(Lp[(int64_t)(c + 1) * ld], xs[c + 1], a1);
-            a2 = fma(Lp[(int64_t)(c + 2) * ld], xs[c + 2], a2);
-            a3 = fma(Lp[(int64_t)(c + 3) * ld], xs[c + 3], a3);
+        const double s = tile_matvec_512(L + row0 + (int64_t)(j - 1) * 128 * ld, ld, xs, red);
+        if (threadIdx.x < 128) {
+            v -= s;
+            b[row0 + r] = v;
         }
-        v -= (a0 + a1) + (a2 + a3);
-        b[row] = v;
-        __syncthreads();
     }
     if (blockIdx.x == 0) {
-        xs[r] = v;
+        if (threadIdx.x < 128) xs[r] = v;
         __syncthreads();
-        const double* ip = inv + (int64_t)R * 128 * 128 + r;
-        double a0 = 0, a1 = 0;
-        for (int c = 0; c < 128; c += 2) {
-            a0 = fma(ip[c * 128], xs[c], a0);
-            a1 = fma(ip[(c + 1) * 128], xs[c + 1], a1);
-        }
-        x[row] = a0 + a1;
+        const double s = tile_matvec_512(inv + (int64_t)R * 128 * 128, 128, xs, red);
+        if (threadIdx.x < 128) x[row0 + r] = s;
     }
 }
 
-// Adjoint (L^T x = b), right-looking from the last block. Launch j = nb-1 .. 0 with grid = j + 1:
+// Adjoint (L^T x = b), from the last block. Launch j = nb-1 .. 0 with grid = j + 1:
 //   (1) when j < nb-1 every block C = blockIdx.x <= j applies the previous solution: b_C -= L[j+1, C]^T x_{j+1};
-//   (2) block C == j solves x_j = inv_j^T b_j.
-__global__ void __launch_bounds__(128)
+//       warp w owns columns 8w .. 8w+7 of the tile, a lane reads rows lane, lane+32, lane+64, lane+96 of each (32
+//       independent loads), then eight shuffle reductions;
+//   (2) block C == j solves x_j = inv_j^T b_j (invT holds the transposed inverse, so it is the same mat-vec as above).
+static __global__ void __launch_bounds__(TRSV_THREADS)
 trsv_adj_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ invT, double* b, double* x, int j,
                 int nb) {
     __shared__ double xs[128];
     __shared__ double bs[128];
-    const int r = threadIdx.x, lane = r & 31, warp = r >> 5;
+    __shared__ double red[512];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Cb = blockIdx.x;
-    bs[r] = b[(int64_t)Cb * 128 + r];
+    if (tid < 128) bs[tid] = b[(int64_t)Cb * 128 + tid];
     if (j < nb - 1) {
-        xs[r] = x[(int64_t)(j + 1) * 128 + r];
+        if (tid < 128) xs[tid] = x[(int64_t)(j + 1) * 128 + tid];
         __syncthreads();
-        for (int cc = 0; cc < 32; ++cc) {
-            const int cl = warp * 32 + cc;
-            const double* Lp = L + (int64_t)(j + 1) * 128 + ((int64_t)Cb * 128 + cl) * ld;
-            double p = Lp[lane] * xs[lane] + Lp[lane + 32] * xs[lane + 32] + Lp[lane + 64] * xs[lane + 64] +
-                       Lp[lane + 96] * xs[lane + 96];
+        const double* Lp = L + (int64_t)(j + 1) * 128 + ((int64_t)Cb * 128 + 8 * warp) * ld + lane;
+        double v[8][4];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[c][k] = __ldcg(Lp + (int64_t)c * ld + 32 * k);
+        const double x0 = xs[lane], x1 = xs[lane + 32], x2 = xs[lane + 64], x3 = xs[lane + 96];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            double p = (v[c][0] * x0 + v[c][1] * x1) + (v[c][2] * x2 + v[c][3] * x3);
             p = warp_sum(p);
-            if (lane == 0) bs[cl] -= p;
+            if (lane == 0) bs[8 * warp + c] -= p;
         }
         __syncthreads();
-        b[(int64_t)Cb * 128 + r] = bs[r];
+        if (tid < 128) b[(int64_t)Cb * 128 + tid] = bs[tid];
     }
     __syncthreads();
     if (Cb == j) {
-        const double* ip = invT + (int64_t)Cb * 128 * 128 + r;
-        double a0 = 0, a1 = 0;
-        for (int c = 0; c < 128; c += 2) {
-            a0 = fma(ip[c * 128], bs[c], a0);
-            a1 = fma(ip[(c + 1) * 128], bs[c + 1], a1);
-        }
-        x[(int64_t)Cb * 128 + r] = a0 + a1;
+        const double s = tile_matvec_512(invT + (int64_t)Cb * 128 * 128, 128, bs, red);
+        if (tid < 128) x[(int64_t)Cb * 128 + tid] = s;
     }
 }
 
@@ -153,7 +174,7 @@ rowreduce_partial_kernel(const double* __restrict__ Bt, int64_t ld, const double
 }
 
 // out[c] = sum_chunks partial ;  with_prior_var: out[c] = k(q_c, q_c) - sum   (mod.rs:266-270)
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 rowreduce_final_kernel(const double* __restrict__ partial, int chunks, int64_t qp, int64_t q, int variance, DevKernel k,
                        const double* __restrict__ qnorm_raw, double* out) {
     const int64_t c = (int64_t)blockIdx.x * 128 + threadIdx.x;
@@ -184,7 +205,7 @@ reduce_kernel(const double* __restrict__ v, const double* __restrict__ w, int64_
     if (threadIdx.x == 0) out[0] = red[0];
 }
 
-__global__ void fill_kernel(double* p, int64_t n, double v) {
+static __global__ void fill_kernel(double* p, int64_t n, double v) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }

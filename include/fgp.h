@@ -120,6 +120,11 @@ int64_t fgp_last_launch_count(const fgp_model* m);
  * Classes: 0 = gemm_nt (SYRK / GEMM / TRSM-as-GEMM, fp64 tensor pipe), 1 = potrf_diag, 2 = pair tiles (Gram,
  * cross-covariance, gradient reductions), 3 = other.  ms / flops / count are arrays of 4. */
 int fgp_set_profiling(fgp_model* m, int on);
+/* Scheduling knobs (results are identical either way; used by bench.py / tests for A-B runs).
+ * FGP_OPT_LOOKAHEAD (default 1): factor the next panel on a second, high-priority stream while the trailing update
+ * of the current one runs. */
+enum fgp_option { FGP_OPT_LOOKAHEAD = 1 };
+int fgp_set_option(fgp_model* m, int option, int64_t value);
 int fgp_profile_summary(const fgp_model* m, double* ms, double* flops, int64_t* count);
 /* Resident-input predict for kernel-only timing: stage queries once, then run the device part repeatedly. */
 int fgp_stage_queries(fgp_model* m, const double* Xq, int64_t ldq, int64_t q);
