@@ -41,6 +41,11 @@ WORKLOADS = {
 }
 
 
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per gemm_nt launch, averaged over the launches of one fit,
+# from the ncu capture named in DESIGN.md "Measurement" (profiles/); None until a capture exists for the workload.
+GEMM_TRAFFIC_BYTES_PER_LAUNCH = {}
+
+
 def fit_flops(n, d):
     return n ** 3 / 3.0 + float(n) * n * d
 
@@ -158,40 +163,60 @@ def run_reference(args, rank, world):
 
 # ----------------------------------------------------------------------------------------------------------------------
 
+def weak_n(world):
+    """Weak scaling: per-GPU Cholesky work n^3/(3N) stays that of n=16384 on one GPU; n is rounded to a whole panel
+    (512 columns).  N=1 -> 16384 (the metric's size), N=2 -> 20480, N=4 -> 26112, N=8 -> 32768 (= config C4's n)."""
+    return int(round(16384.0 * world ** (1.0 / 3.0) / 512.0)) * 512
+
+
 def run_ours(args, rank, local_rank, world):
+    dist = None
+    if world > 1:
+        import torch  # before the native library: see csrc/nccl_dyn.cuh
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("gloo")  # plumbing only: NCCL id exchange, barriers, max over ranks
     from friedrich_b200 import _native as N
+    from friedrich_b200 import sharded
     from friedrich_b200.kernels import SquaredExp
     from friedrich_b200.synthetic import make_dataset, make_inputs
 
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
     n, d, q, _, desc = WORKLOADS[args.workload]
+    use_sharded = world > 1 or args.sharded
+    if world > 1 and args.workload == "metric":
+        n = weak_n(world)
+        desc = f"fit: Gram+Cholesky n={n} d={d} SquaredExp f64 sharded over {world} GPUs (n = 16384*N^(1/3)); predict q={q}"
     lib = N.lib()
     h = N.Handle(local_rank)
-    Xs, ys = make_dataset(0x5EED0001 + rank, n, d)
-    Xqs = make_inputs(0x5EED0002 + rank, q, d)
+    if use_sharded:
+        sharded.comm_init(h, rank, world, dist)
+    Xs, ys = make_dataset(0x5EED0001, n, d)
+    qr = q // world  # queries are independent: each rank predicts its slice against the replicated factor
+    Xqs = make_inputs(0x5EED0002, q, d)[rank * qr:(rank + 1) * qr]
     X, pX = pinned_array(N, (n, d))
     y, py = pinned_array(N, (n,))
-    Xq, pq = pinned_array(N, (q, d))
+    Xq, pq = pinned_array(N, (qr, d))
     X[...], y[...], Xq[...] = Xs, ys, Xqs
-    mean, pm = pinned_array(N, (q,))
-    var, pv = pinned_array(N, (q,))
+    mean, pm = pinned_array(N, (qr,))
+    var, pv = pinned_array(N, (qr,))
     kd = SquaredExp(math.sqrt(d / 6.0), 1.0).device_desc()
     noise = 0.1
 
     def fit_host():
-        h.check(lib.fgp_fit(h.ptr, N.dptr(X), n, n, d, N.dptr(y), C.byref(kd), noise, 0, 0.0))
+        if use_sharded:  # rank 0's host X, y -> H2D -> ncclBroadcast -> sharded factorisation
+            h.check(lib.fgp_fit_sharded(h.ptr, N.dptr(X) if rank == 0 else None, n, n, d, N.dptr(y) if rank == 0 else None,
+                                        C.byref(kd), noise, 0, 0.0))
+        else:
+            h.check(lib.fgp_fit(h.ptr, N.dptr(X), n, n, d, N.dptr(y), C.byref(kd), noise, 0, 0.0))
 
     def refit():
-        h.check(lib.fgp_refit(h.ptr, C.byref(kd), noise, 0, 0.0))
+        if use_sharded:
+            h.check(lib.fgp_refit_sharded(h.ptr, C.byref(kd), noise, 0, 0.0))
+        else:
+            h.check(lib.fgp_refit(h.ptr, C.byref(kd), noise, 0, 0.0))
 
     def predict_host():
-        h.check(lib.fgp_predict_mean_var(h.ptr, C.byref(kd), N.dptr(Xq), q, q, N.dptr(mean), N.dptr(var)))
+        h.check(lib.fgp_predict_mean_var(h.ptr, C.byref(kd), N.dptr(Xq), qr, qr, N.dptr(mean), N.dptr(var)))
 
     def predict_staged():
         h.check(lib.fgp_predict_staged(h.ptr, C.byref(kd), 1, 1))
@@ -206,7 +231,7 @@ def run_ours(args, rank, local_rank, world):
         if dist is None:
             return v
         import torch
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        t = torch.tensor([v], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
@@ -236,18 +261,19 @@ def run_ours(args, rank, local_rank, world):
         tcnt += pcnt
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
+    # collective steps start together (the first panel broadcast synchronises the ranks), so the slowest rank's device
+    # time per step is the job's time per step; wall_ms (barrier to barrier, host clock) is reported beside it
     fit_ms = max_over_ranks(dev_ms / args.steps)
+    wall_ms = max_over_ranks(wall_ms)
 
     # ---- predict throughput, queries resident ------------------------------------------------------------------------
-    h.check(lib.fgp_stage_queries(h.ptr, N.dptr(Xq), q, q))
+    h.check(lib.fgp_stage_queries(h.ptr, N.dptr(Xq), qr, qr))
     for _ in range(args.warmup):
         predict_staged()
     pred_ms = 0.0
-    pred_launches = 0
     for _ in range(args.steps):
         predict_staged()
         pred_ms += h.last_device_ms()
-        pred_launches += h.last_launch_count()
     pred_ms = max_over_ranks(pred_ms / args.steps)
 
     # ---- timed region 2: end to end through the C-ABI with host buffers -------------------------------------------------
@@ -265,39 +291,51 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
     clocks = sampler.stop()
+    bcast_mb = lib.fgp_comm_last_bytes(h.ptr) / 1e6 if use_sharded else 0.0
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    value = world * fit_flops(n, d) / (fit_ms * 1e-3) * 1e-12
+    value = fit_flops(n, d) / (fit_ms * 1e-3) * 1e-12
     gemm_tflops = tfl[0] / (tms[0] * 1e-3) * 1e-12 if tms[0] > 0 else None
     line = {
         "metric": "gp_fit_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": fit_ms, "higher_is_better": True,
-        "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "weak" if (world > 1 and args.workload == "metric") else "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
         "config": {"workload": desc, "n": n, "d": d, "q": q, "noise": noise, "kernel": "SquaredExp(ls=sqrt(d/6), ampl=1)",
                    "l2": "inputs larger than L2 (factor = %.2f GB)" % (8.0 * n * n / 1e9),
-                   "multi_gpu": "independent replicas" if world > 1 else "single GPU"},
+                   "multi_gpu": ("block-cyclic 512-column panels, NCCL panel broadcast, replicated factor; "
+                                 "queries sharded") if use_sharded else "single GPU",
+                   "lookahead": not args.no_lookahead},
         "frac_of_fp64_peak": value / (world * FP64_PEAK_TFLOPS),
-        "predict_qps": world * q / (pred_ms * 1e-3), "predict_ms": pred_ms,
+        "predict_qps": q / (pred_ms * 1e-3), "predict_ms": pred_ms,
         "wall_ms_per_step": wall_ms / args.steps,
-        "e2e": {"value": world * (fit_flops(n, d) + predict_flops(n, d, q)) / (e2e_ms * 1e-3) * 1e-12, "unit": "TFLOP/s",
+        "e2e": {"value": (fit_flops(n, d) + world * predict_flops(n, d, qr)) / (e2e_ms * 1e-3) * 1e-12, "unit": "TFLOP/s",
                 "ms_per_step": e2e_ms, "fit_ms": e2e_fit_ms / args.steps,
                 "predict_qps": q / max((e2e_ms - e2e_fit_ms / args.steps) * 1e-3, 1e-9),
                 "h2d_bytes_per_step": 8 * (n * d + n + q * d), "d2h_bytes_per_step": 8 * 2 * q,
-                "what": "fgp_fit(host X, y) + fgp_predict_mean_var(host Xq) -> host mean, var"},
+                "what": ("fgp_fit_sharded(rank-0 host X, y) + " if use_sharded else "fgp_fit(host X, y) + ") +
+                        "fgp_predict_mean_var(host Xq) -> host mean, var"},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "gemm_nt_kernel", "bound": "tensor", "achieved": gemm_tflops, "peak": FP64_PEAK_TFLOPS,
                      "unit": "TFLOP/s", "frac": (gemm_tflops / FP64_PEAK_TFLOPS) if gemm_tflops else None,
-                     "traffic": None, "launches": int(tcnt[0]), "share_of_step": float(tms[0] / max(dev_ms, 1e-9)),
+                     "traffic": GEMM_TRAFFIC_BYTES_PER_LAUNCH.get(args.workload) if world == 1 else None,
+                     "launches": int(tcnt[0]), "share_of_step": float(tms[0] / max(dev_ms, 1e-9)),
+                     "note": "rank 0; achieved = algorithmic flops of all gemm_nt launches / sum of their CUDA-event "
+                             "durations (with look-ahead the panel-stream launches overlap the main-stream ones, so "
+                             "share_of_step can exceed 1)",
                      "peak_source": "fp64 DMMA m8n8k4 register-resident burst measured on this pool "
-                                    "(MEASURED_PEAKS.json has no fp64 figure; nominal 148 SM x 128 flop/clk x 1.965 GHz = 37.2)"},
+                                    "(profiles/fp64_peak_r01.jsonl; MEASURED_PEAKS.json has no fp64 figure; nominal "
+                                    "148 SM x 128 flop/clk x 1.965 GHz = 37.2; sustained DMMA loop 27.4)"},
         "kernel_ms_per_step": {"gemm_nt": tms[0] / args.steps, "potrf_diag": tms[1] / args.steps,
                                "gram": tms[2] / args.steps},
         "clocks": clocks,
     }
+    if use_sharded:
+        line["nccl_bcast_mb_per_step"] = bcast_mb
     if world == 1 and not args.no_cpu_baseline:
         ns, qs = (4096, 256) if n >= 4096 else (n, min(q, 256))
         dt, flops = time_oracle(ns, d, qs, 1, 0)
@@ -321,6 +359,7 @@ def main():
     ap.add_argument("--workload", default="metric", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lookahead", action="store_true", help="A/B: single-stream Cholesky schedule")
+    ap.add_argument("--sharded", action="store_true", help="use the collective entry points even on one GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -18,6 +18,7 @@ MAX_OPS = 15
 MAX_PARAMS = 24
 
 FGP_OPT_LOOKAHEAD = 1
+FGP_COMM_ID_BYTES = 128
 FGP_OK, FGP_ERR_NOT_POSDEF, FGP_ERR_BAD_ARG, FGP_ERR_BAD_KERNEL, FGP_ERR_CUDA, FGP_ERR_NOT_FITTED, FGP_ERR_COMM = range(7)
 
 
@@ -84,9 +85,17 @@ SIGNATURES = {
     "fgp_stage_queries": (C.c_int, [_h, _dp, _i64, _i64]),
     "fgp_predict_staged": (C.c_int, [_h, _kd, C.c_int, C.c_int]),
     "fgp_fetch_predictions": (C.c_int, [_h, _dp, _dp]),
+    "fgp_comm_unique_id": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "fgp_comm_init_rank": (C.c_int, [_h, C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
+    "fgp_comm_destroy": (C.c_int, [_h]),
+    "fgp_fit_sharded": (C.c_int, [_h, _dp, _i64, _i64, _i64, _dp, _kd, C.c_double, C.c_int, C.c_double]),
+    "fgp_refit_sharded": (C.c_int, [_h, _kd, C.c_double, C.c_int, C.c_double]),
+    "fgp_shard_plan": (C.c_int, [_i64, C.c_int, C.c_int, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), _dp]),
+    "fgp_comm_last_bytes": (C.c_double, [_h]),
     "fgp_alloc_pinned": (C.c_void_p, [C.c_size_t]),
     "fgp_free_pinned": (None, [C.c_void_p]),
     "fgp_cholesky_lower": (C.c_int, [C.c_int, _dp, _i64, _i64, C.POINTER(_i64)]),
+    "fgp_dbg_lower_tiles": (_i64, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _i64]),
     "fgp_dbg_gemm_nt": (C.c_int, [C.c_int, _dp, _i64, _dp, _i64, _dp, _i64, C.c_int, C.c_int, C.c_int, C.c_double,
                                   C.c_int, C.c_int]),
 }

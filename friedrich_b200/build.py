@@ -1,5 +1,5 @@
 """In-tree build of libfgp_sm100.so: plain `nvcc` of the .cu sources for sm_100a (no PyTorch, no cuBLAS / cuSOLVER; the
-only libraries linked are the CUDA runtime and — for the multi-GPU path — NCCL).  Each .cu is its own translation unit
+only library linked is the CUDA runtime; NCCL is dlopen()ed by the multi-GPU path).  Each .cu is its own translation unit
 (no relocatable device code: kernels are only launched from the TU that defines them); the TUs compile in parallel."""
 from __future__ import annotations
 
@@ -16,7 +16,7 @@ LIB = os.path.join(_HERE, "libfgp_sm100.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden"]
-LINK_LIBS = ["-lnccl"]
+LINK_LIBS = ["-ldl"]  # NCCL is dlopen()ed on the first multi-GPU call (csrc/nccl_dyn.cuh)
 
 
 def _nvcc():

@@ -24,6 +24,7 @@
 #include "trsm.cuh"
 #include "lml.cuh"
 #include "covariance.cuh"
+#include "sharded.cuh"
 
 using namespace fgp;
 
@@ -215,6 +216,21 @@ int predict_common(fgp_model* m, const fgp_kernel_desc* kd, const double* Xq, in
 
 }  // namespace
 
+namespace {
+void comm_release(fgp_model* m) {
+    fgp_comm* c = m->comm;
+    if (!c) return;
+    if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
+    c->pbuf[0].release();
+    c->pbuf[1].release();
+    if (c->ev_bcast) cudaEventDestroy(c->ev_bcast);
+    for (cudaEvent_t e : c->ev_trail)
+        if (e) cudaEventDestroy(e);
+    delete c;
+    m->comm = nullptr;
+}
+}  // namespace
+
 // =================================================================================================================
 // lifecycle
 FGP_EXPORT const char* fgp_version(void) { return "libfgp_sm100 0.1 (sm_100a, fp64 DMMA + TMA)"; }
@@ -252,6 +268,7 @@ FGP_EXPORT int fgp_destroy(fgp_model* m) {
         DeviceGuard dg(m->device);
         if (m->st) cudaStreamSynchronize(m->st);
         if (m->st2) cudaStreamSynchronize(m->st2);
+        comm_release(m);
         for (DevBuf* b : {&m->xr, &m->xc, &m->nc, &m->nr, &m->cmean, &m->y, &m->z, &m->alpha, &m->work, &m->L, &m->inv,
                           &m->invT, &m->staging, &m->qr, &m->qc, &m->qnc, &m->qnr, &m->bt, &m->partial, &m->mean_d,
                           &m->var_d, &m->scalars, &m->kqq, &m->U, &m->Kinv, &m->lml_partial})
@@ -319,8 +336,8 @@ FGP_EXPORT void fgp_free_pinned(void* p) {
 // fit
 namespace {
 // EMatrix::new + Input::into_dmatrix (mod.rs:142-148): make the training inputs resident (row-major, padded, centred)
-int set_inputs(fgp_model* m, const double* X, int64_t ldx, int64_t n, int64_t d) {
-    if (!X || n <= 0 || d <= 0 || ldx < n) return fail(m, FGP_ERR_BAD_ARG, "bad training matrix");
+int reserve_inputs(fgp_model* m, int64_t n, int64_t d) {
+    if (n <= 0 || d <= 0) return fail(m, FGP_ERR_BAD_ARG, "bad training matrix");
     m->fitted = false;
     const int64_t np = round_up(n, TILE), dp = round_up(d, 4);
     if (np > m->cap || dp != m->dp) {
@@ -333,12 +350,24 @@ int set_inputs(fgp_model* m, const double* X, int64_t ldx, int64_t n, int64_t d)
     m->d = d;
     m->dp = dp;
     m->np = np;
-    FGP_TRY(upload_colmajor(m, X, ldx, n, d));
-    col_mean_kernel<<<(unsigned)d, 256, 0, m->st>>>(m->staging.p, n, n, m->cmean.p);
-    convert_points_kernel<<<(unsigned)((np + 255) / 256), 256, 0, m->st>>>(m->staging.p, n, n, (int)d, (int)dp, m->cmean.p,
-                                                                          0, np, m->xr.p, m->xc.p, m->nc.p, m->nr.p);
+    CU(m, m->staging.reserve((size_t)n * d));
+    return FGP_OK;
+}
+// staging (n x d column-major, ld = n) -> padded row-major raw / centred points and their norms
+int convert_staged_inputs(fgp_model* m) {
+    const int64_t n = m->n, np = m->np;
+    col_mean_kernel<<<(unsigned)m->d, 256, 0, m->st>>>(m->staging.p, n, n, m->cmean.p);
+    convert_points_kernel<<<(unsigned)((np + 255) / 256), 256, 0, m->st>>>(m->staging.p, n, n, (int)m->d, (int)m->dp,
+                                                                          m->cmean.p, 0, np, m->xr.p, m->xc.p, m->nc.p, m->nr.p);
     m->launches += 2;
-    CU(m, cudaMemsetAsync(m->y.p, 0, np * sizeof(double), m->st));
+    return FGP_OK;
+}
+int set_inputs(fgp_model* m, const double* X, int64_t ldx, int64_t n, int64_t d) {
+    if (!X || n <= 0 || d <= 0 || ldx < n) return fail(m, FGP_ERR_BAD_ARG, "bad training matrix");
+    FGP_TRY(reserve_inputs(m, n, d));
+    FGP_TRY(upload_colmajor(m, X, ldx, n, d));
+    FGP_TRY(convert_staged_inputs(m));
+    CU(m, cudaMemsetAsync(m->y.p, 0, m->np * sizeof(double), m->st));
     return FGP_OK;
 }
 }  // namespace
@@ -660,6 +689,165 @@ FGP_EXPORT int fgp_cholesky_lower(int device, double* A, int64_t lda, int64_t n,
     for (int64_t c = 1; c < n; ++c)
         for (int64_t r = 0; r < c; ++r) A[r + c * lda] = 0.0;
     return FGP_OK;
+}
+
+// =================================================================================================================
+// multi-GPU: one process per GPU, NCCL panel broadcasts (sharded.cu)
+FGP_EXPORT int fgp_comm_unique_id(void* id_out, size_t bytes) {
+    if (!id_out || bytes < sizeof(ncclUniqueId)) return FGP_ERR_BAD_ARG;
+    ncclUniqueId id;
+    const NcclApi* nccl = nccl_api();
+    if (!nccl || nccl->GetUniqueId(&id) != ncclSuccess) return FGP_ERR_COMM;
+    std::memset(id_out, 0, bytes);
+    std::memcpy(id_out, &id, sizeof(id));
+    return FGP_OK;
+}
+
+FGP_EXPORT int fgp_comm_init_rank(fgp_model* m, const void* id, size_t bytes, int nranks, int rank) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (!id || bytes < sizeof(ncclUniqueId) || nranks < 1 || rank < 0 || rank >= nranks)
+        return fail(m, FGP_ERR_BAD_ARG, "bad communicator arguments");
+    comm_release(m);
+    fgp_comm* c = new (std::nothrow) fgp_comm();
+    if (!c) return fail(m, FGP_ERR_CUDA, "out of host memory");
+    c->nranks = nranks;
+    c->rank = rank;
+    m->comm = c;
+    if (cudaEventCreateWithFlags(&c->ev_bcast, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_trail[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_trail[1], cudaEventDisableTiming) != cudaSuccess) {
+        comm_release(m);
+        return fail(m, FGP_ERR_CUDA, "event creation failed");
+    }
+    if (nranks > 1) {
+        const NcclApi* nccl = nccl_api();
+        if (!nccl) {
+            comm_release(m);
+            return fail(m, FGP_ERR_COMM, "libnccl.so.2 could not be loaded");
+        }
+        ncclUniqueId uid;
+        std::memcpy(&uid, id, sizeof(uid));
+        ncclResult_t r = nccl->CommInitRank(&c->comm, nranks, uid, rank);
+        if (r != ncclSuccess) {
+            std::string msg = std::string("ncclCommInitRank: ") + nccl->GetErrorString(r);
+            comm_release(m);
+            return fail(m, FGP_ERR_COMM, msg);
+        }
+    }
+    return FGP_OK;
+}
+
+FGP_EXPORT int fgp_comm_destroy(fgp_model* m) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    comm_release(m);
+    return FGP_OK;
+}
+
+FGP_EXPORT double fgp_comm_last_bytes(const fgp_model* m) { return (m && m->comm) ? m->comm->bcast_bytes : 0.0; }
+
+// Host-only description of the block-cyclic plan (no GPU needed): panel width in columns, number of panels, how many this
+// rank owns and its share of the trailing-update flops.
+FGP_EXPORT int fgp_shard_plan(int64_t n, int nranks, int rank, int64_t* panel_cols, int64_t* n_panels, int64_t* n_owned,
+                              double* flop_share) {
+    if (n <= 0 || nranks < 1 || rank < 0 || rank >= nranks) return FGP_ERR_BAD_ARG;
+    const int64_t np = round_up(n, TILE), nb = np / TILE, NP = (nb + PANEL_TILES - 1) / PANEL_TILES;
+    int64_t owned = 0;
+    double mine = 0.0, total = 0.0;
+    for (int64_t p = 0; p < NP; ++p) {
+        const double rows = (double)(np - p * PANEL_TILES * TILE);
+        const double w = (double)std::min<int64_t>(PANEL_TILES * TILE, np - p * PANEL_TILES * TILE);
+        const double f = rows * w * (double)(p * PANEL_TILES * TILE);  // updates this panel receives from the p panels before it
+        total += f;
+        if (shard_owner(p, nranks) == rank) {
+            owned += 1;
+            mine += f;
+        }
+    }
+    if (panel_cols) *panel_cols = PANEL_TILES * TILE;
+    if (n_panels) *n_panels = NP;
+    if (n_owned) *n_owned = owned;
+    if (flop_share) *flop_share = total > 0.0 ? mine / total : (rank == 0 ? 1.0 : 0.0);
+    return FGP_OK;
+}
+
+namespace {
+int finish_sharded(fgp_model* m, int rc) {
+    if (rc != FGP_OK) return rc;
+    CU(m, cudaMemcpyAsync(m->info_h, m->info_d, sizeof(int), cudaMemcpyDeviceToHost, m->st));
+    solve_alpha(m);
+    CU(m, cudaStreamSynchronize(m->st));
+    CU(m, cudaGetLastError());
+    if (*m->info_h != 0) {
+        m->failed_col = *m->info_h - 1;
+        m->fitted = false;
+        return fail(m, FGP_ERR_NOT_POSDEF, "Cholesky decomposition failed at column " + std::to_string(m->failed_col));
+    }
+    m->failed_col = -1;
+    m->fitted = true;
+    return FGP_OK;
+}
+}  // namespace
+
+// Same contract as fgp_fit, called by EVERY rank of the communicator. X / y_resid are read on rank 0 only (other ranks may
+// pass NULL) and reach the other GPUs by ncclBroadcast; every rank ends with the complete factor and alpha.
+FGP_EXPORT int fgp_fit_sharded(fgp_model* m, const double* X, int64_t ldx, int64_t n, int64_t d, const double* y_resid,
+                               const fgp_kernel_desc* kernel, double noise, int has_eps, double eps) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (!m->comm) return fail(m, FGP_ERR_COMM, "fgp_comm_init_rank has not been called");
+    const bool root = m->comm->rank == 0;
+    if (root && (!X || !y_resid || ldx < n)) return fail(m, FGP_ERR_BAD_ARG, "rank 0 must supply X and y_resid");
+    if (!(noise >= 0.0)) return fail(m, FGP_ERR_BAD_ARG, "The noise parameter should non-negative");
+    KernelTraits kt;
+    FGP_TRY(check_kernel(m, kernel, &kt));
+    begin_timed(m);
+    FGP_TRY(reserve_inputs(m, n, d));
+    CU(m, cudaMemsetAsync(m->y.p, 0, m->np * sizeof(double), m->st));
+    if (root) {
+        FGP_TRY(upload_colmajor(m, X, ldx, n, d));
+        CU(m, cudaMemcpyAsync(m->y.p, y_resid, n * sizeof(double), cudaMemcpyHostToDevice, m->st));
+    }
+    if (m->comm->nranks > 1) {
+        const NcclApi* nccl = nccl_api();
+        if (!nccl || nccl->Broadcast(m->staging.p, m->staging.p, (size_t)n * d, ncclDouble, 0, m->comm->comm, m->st) != ncclSuccess ||
+            nccl->Broadcast(m->y.p, m->y.p, (size_t)n, ncclDouble, 0, m->comm->comm, m->st) != ncclSuccess)
+            return fail(m, FGP_ERR_COMM, "ncclBroadcast of the training set failed");
+    }
+    FGP_TRY(convert_staged_inputs(m));
+    int rc = finish_sharded(m, factor_sharded(m, kernel, kt, noise, has_eps, eps));
+    int rc2 = end_timed(m);
+    return rc != FGP_OK ? rc : rc2;
+}
+
+FGP_EXPORT int fgp_refit_sharded(fgp_model* m, const fgp_kernel_desc* kernel, double noise, int has_eps, double eps) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (!m->comm) return fail(m, FGP_ERR_COMM, "fgp_comm_init_rank has not been called");
+    if (m->n <= 0) return fail(m, FGP_ERR_NOT_FITTED, "no resident training set");
+    if (!(noise >= 0.0)) return fail(m, FGP_ERR_BAD_ARG, "The noise parameter should non-negative");
+    KernelTraits kt;
+    FGP_TRY(check_kernel(m, kernel, &kt));
+    begin_timed(m);
+    int rc = finish_sharded(m, factor_sharded(m, kernel, kt, noise, has_eps, eps));
+    int rc2 = end_timed(m);
+    return rc != FGP_OK ? rc : rc2;
+}
+
+// =================================================================================================================
+// test hook (host only, no GPU): the block -> tile map of the lower-mode GEMM launches, see lower_tile_decode
+FGP_EXPORT int64_t fgp_dbg_lower_tiles(int M, int N, int grp, int stride, int* ti_out, int* tj_out, int64_t capacity) {
+    GemmArgs g{};
+    g.M = M; g.N = N; g.K = GEMM_KC; g.lower = 1; g.grp = grp; g.stride = stride;
+    const int64_t tiles = gemm_nt_tiles(g);
+    for (int64_t b = 0; b < tiles && b < capacity; ++b)
+        lower_tile_decode(M / GEMM_BM, std::max(grp, 1), std::max(stride, 1), (int)b, ti_out[b], tj_out[b]);
+    return tiles;
 }
 
 // =================================================================================================================

@@ -1,6 +1,8 @@
 // gemm_nt.cu — the fp64 tensor-pipe NT GEMM kernel (see gemm_nt.cuh for the contract and the execution model).
 #include "gemm_nt.cuh"
 
+#include <algorithm>
+
 namespace fgp {
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(GemmArgs g) {
@@ -15,14 +17,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(GemmArgs g) {
         const int tm = g.M / GEMM_BM;
         int b = blockIdx.x;
         if (g.lower) {
-            // column tj holds (tm - tj) tiles; find tj with prefix(tj) <= b < prefix(tj+1), prefix(j) = j*tm - j(j-1)/2
-            double tmf = (double)tm + 0.5;
-            int j = (int)(tmf - sqrt(tmf * tmf - 2.0 * (double)b));
-            if (j < 0) j = 0;
-            while (j > 0 && (int64_t)j * tm - (int64_t)j * (j - 1) / 2 > b) --j;
-            while ((int64_t)(j + 1) * tm - (int64_t)(j + 1) * j / 2 <= b) ++j;
-            tj = j;
-            ti = j + (b - (int)((int64_t)j * tm - (int64_t)j * (j - 1) / 2));
+            lower_tile_decode(tm, max(g.grp, 1), max(g.stride, 1), b, ti, tj);
         } else {
             ti = b % tm;
             tj = b / tm;
@@ -141,22 +136,32 @@ cudaError_t gemm_nt_prepare() {
     return e;
 }
 
+int64_t gemm_nt_tiles(const GemmArgs& g) {
+    const int64_t tm = g.M / GEMM_BM, tn = g.N / GEMM_BN;
+    if (!g.lower) return tm * tn;
+    const int64_t PT = std::max(g.grp, 1), S = std::max(g.stride, 1);
+    int64_t tiles = 0;
+    for (int64_t jl = 0; jl < tn; ++jl) {  // local tile column jl sits at tile column (jl / PT) * S + jl % PT
+        const int64_t tj = (jl / PT) * S + jl % PT;
+        if (tm - tj > 0) tiles += tm - tj;
+    }
+    return tiles;
+}
+
 double gemm_nt_flops(const GemmArgs& g) {
-    const double tm = g.M / GEMM_BM, tn = g.N / GEMM_BN;
     if (g.k_from_tile) {  // U U^T on upper-triangular operands: tile (i, j<=i) contracts over K - 128 i
+        const int tm = g.M / GEMM_BM;
         double f = 0.0;
-        for (int i = 0; i < (int)tm; ++i) f += (double)(i + 1) * (g.K - GEMM_BM * i);
+        for (int i = 0; i < tm; ++i) f += (double)(i + 1) * (g.K - GEMM_BM * i);
         return 2.0 * GEMM_BM * GEMM_BN * f;
     }
-    const double tiles = g.lower ? tn * tm - tn * (tn - 1) / 2 : tm * tn;  // lower: trapezoid of tn tile columns
-    return 2.0 * GEMM_BM * GEMM_BN * tiles * g.K;
+    return 2.0 * GEMM_BM * GEMM_BN * (double)gemm_nt_tiles(g) * g.K;
 }
 
 int64_t gemm_nt_launch(const GemmArgs& g, const LaunchCtx& ctx) {
-    if (g.M <= 0 || g.N <= 0) return 0;
-    const int64_t tm = g.M / GEMM_BM, tn = g.N / GEMM_BN;
-    const int64_t tiles = g.lower ? tn * tm - tn * (tn - 1) / 2 : tm * tn;
-    if (g.K <= 0) return 0;
+    if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
+    const int64_t tiles = gemm_nt_tiles(g);
+    if (tiles <= 0) return 0;
     ProfScope ps(ctx, PROF_GEMM, gemm_nt_flops(g));
     gemm_nt_kernel<<<(unsigned)tiles, GEMM_THREADS, GEMM_SMEM_BYTES, ctx.st>>>(g);
     return tiles;

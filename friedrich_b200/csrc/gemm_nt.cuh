@@ -40,10 +40,39 @@ struct GemmArgs {
     int beta_one;    // 1: C += alpha*A*B^T ; 0: C = alpha*A*B^T
     int lower;       // 1: only tiles on or below the diagonal are computed (N <= M: the first N/128 tile columns of the
                      //    triangle), diagonal tiles store r >= c only
+    int grp, stride; // lower mode: the N/128 tile columns computed are groups of `grp` consecutive tile columns whose starts
+                     //    are `stride` tile columns apart (0,0 = contiguous); rows/columns are relative to C, whose origin
+                     //    is on the diagonal
     int k_from_tile; // 1: contraction starts at k = 128*max(tile_row, tile_col) (operands upper-triangular: U U^T)
 };
 
+// Lower mode: linear block index b -> tile (ti, tj), both relative to C (whose origin is on the diagonal).
+// Tile columns come in groups of PT consecutive columns, group q starting at tile column q*S (S = PT: the plain triangle /
+// trapezoid; S = P*PT: the panels one rank owns under the block-cyclic distribution).  Column tj holds the (tm - tj) tiles
+// on or below the diagonal; blocks enumerate them column by column.
+__host__ __device__ inline void lower_tile_decode(int tm, int PT, int S, int b, int& ti, int& tj) {
+    const double a = (double)PT * tm - 0.5 * PT * (PT - 1), c2 = 0.5 * S * PT;
+    const double disc = (a + c2) * (a + c2) - 4.0 * c2 * (double)b;
+    int gi = (int)(((a + c2) - sqrt(disc > 0.0 ? disc : 0.0)) / (2.0 * c2));
+    if (gi < 0) gi = 0;
+    auto prefix = [&](int q) -> int64_t {  // tiles in groups 0 .. q-1
+        return (int64_t)q * PT * tm - (int64_t)q * (PT * (PT - 1) / 2) - (int64_t)S * PT * ((int64_t)q * (q - 1) / 2);
+    };
+    while (gi > 0 && prefix(gi) > b) --gi;
+    while (tm - (int64_t)(gi + 1) * S > 0 && prefix(gi + 1) <= b) ++gi;
+    int rem = b - (int)prefix(gi);
+    int w = 0;
+    for (; w < PT - 1; ++w) {
+        const int cnt = tm - gi * S - w;
+        if (rem < cnt) break;
+        rem -= cnt;
+    }
+    tj = gi * S + w;
+    ti = tj + rem;
+}
+
 // defined in gemm_nt.cu
+int64_t gemm_nt_tiles(const GemmArgs& g);  // number of 128x128 tiles one launch computes
 cudaError_t gemm_nt_prepare();
 // algorithmic flops of one launch (what the roofline figure in bench.py is computed from)
 double gemm_nt_flops(const GemmArgs& g);

@@ -30,6 +30,8 @@ struct PairArgs {
     int dp;
     int64_t rows, cols;  // padded extents (multiples of 128 / 64)
     int row_tile0;       // first 128-row tile visited (add_samples only rebuilds the last block rows)
+    int col_tile0;       // first 64-column tile visited and how many (0 = all): the sharded fit assembles only the block
+    int col_tiles;       // columns a rank owns
     int symmetric;       // rows and columns are the same point set: only r >= c is visited
 };
 
@@ -41,7 +43,7 @@ constexpr int PAIR_TN = 64;   // tile columns
 template <int MODE, class Epi>
 __global__ void __launch_bounds__(256) pair_tile_kernel(PairArgs a, Epi epi) {
     const int64_t row0 = (int64_t)(blockIdx.x + a.row_tile0) * PAIR_TM;
-    const int64_t col0 = (int64_t)blockIdx.y * PAIR_TN;
+    const int64_t col0 = (int64_t)(blockIdx.y + a.col_tile0) * PAIR_TN;
     const bool active = !(a.symmetric && row0 + PAIR_TM - 1 < col0);
     if (active) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -132,7 +134,8 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(PairArgs a, Epi epi) {
 }
 
 inline dim3 pair_grid(const PairArgs& pa) {
-    return dim3((unsigned)(pa.rows / PAIR_TM - pa.row_tile0), (unsigned)(pa.cols / PAIR_TN));
+    return dim3((unsigned)(pa.rows / PAIR_TM - pa.row_tile0),
+                (unsigned)(pa.col_tiles > 0 ? pa.col_tiles : pa.cols / PAIR_TN - pa.col_tile0));
 }
 
 // Deterministic block reduction used by accumulating epilogues: sums NV per-thread values over the 256 threads of

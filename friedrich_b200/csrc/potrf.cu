@@ -164,7 +164,7 @@ cudaError_t potrf_prepare() {
 }
 
 // block columns [J, Jend) of one panel, left-looking inside the panel; every launch goes to c.st
-static void factor_panel(double* A, int64_t lda, int64_t np, int64_t J, int64_t Jend, double* invdiag, double* invdiagT,
+void factor_panel(double* A, int64_t lda, int64_t np, int64_t J, int64_t Jend, double* invdiag, double* invdiagT,
                          int has_sub, double sub, int* info, const LaunchCtx& c, PotrfCounters* cnt) {
     const int64_t nb = np / TILE;
     for (int64_t j = J; j < Jend; ++j) {
@@ -198,7 +198,7 @@ static void factor_panel(double* A, int64_t lda, int64_t np, int64_t J, int64_t 
 }
 
 // trailing block columns [c0, c1) (rows >= c0, trapezoid on/below the diagonal) -= P P^T restricted to them, P = panel [J, Jend)
-static void trailing_update(double* A, int64_t lda, int64_t np, int64_t J, int64_t Jend, int64_t c0, int64_t c1,
+void trailing_update(double* A, int64_t lda, int64_t np, int64_t J, int64_t Jend, int64_t c0, int64_t c1,
                             const LaunchCtx& c, PotrfCounters* cnt) {
     if (c0 >= c1) return;
     GemmArgs g{};

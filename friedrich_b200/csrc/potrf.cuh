@@ -31,6 +31,13 @@ cudaError_t potrf_prepare();
 // Factor block columns [jb_begin, np/128) of the np x np matrix A (ld = lda) in place. Block columns before
 // jb_begin must already hold final factor values in ALL rows (used by add_samples: the caller has applied them to
 // the trailing block). invdiag / invdiagT: [np/128][128*128] (inverse blocks and their transposes). info: device int, 0 on entry.
+// block columns [J, Jend) of one panel (left-looking inside the panel: update, diagonal tile, panel solve); launches on c.st
+void factor_panel(double* A, int64_t lda, int64_t np, int64_t J, int64_t Jend, double* invdiag, double* invdiagT,
+                  int has_sub, double sub, int* info, const LaunchCtx& c, PotrfCounters* cnt);
+// trailing block columns [c0, c1) (rows >= c0: the trapezoid on/below the diagonal) -= P P^T, P = block columns [J, Jend)
+void trailing_update(double* A, int64_t lda, int64_t np, int64_t J, int64_t Jend, int64_t c0, int64_t c1,
+                     const LaunchCtx& c, PotrfCounters* cnt);
+
 // `la` (optional): a second, high-priority stream and two events for the one-panel look-ahead schedule; null => everything
 // runs on st.st in program order.
 struct PotrfLookahead {

@@ -1,0 +1,155 @@
+// sharded.cu — see sharded.cuh.  Schedule per rank r of P, for panel p = 0 .. NP-1 (owner = p % P):
+//
+//   panel stream (high priority)                                   main stream
+//   ---------------------------------------------------------      ------------------------------------------------
+//   wait: trailing update p-2 done (buffer p&1 free, my panel
+//         p has every update up to p-2)
+//   owner: look-ahead update of panel p by panel p-1 (buffer)
+//          factor panel p (update / diagonal tile / panel solve)
+//          pack rows >= p*512 of the panel into buffer p&1
+//   ncclBroadcast(buffer p&1, root = owner)            ---->      wait: panel p arrived
+//                                                                  update every owned panel c > p (except c = p+1:
+//                                                                  that is the owner's look-ahead above) from the buffer
+//                                                                  non-owners: unpack the buffer into their copy of L
+//
+// so the factorisation + broadcast of panel p+1 overlaps the trailing updates by panel p on all ranks, and when the loop
+// ends every rank holds the whole factor (replicated L: alpha solve and predict run locally, queries shard trivially).
+#include "sharded.cuh"
+
+#include <algorithm>
+#include <string>
+
+#include "covariance.cuh"
+#include "gemm_nt.cuh"
+
+namespace fgp {
+
+#define NC(m, call)                                                                                                \
+    do {                                                                                                           \
+        ncclResult_t r__ = (call);                                                                                 \
+        if (r__ != ncclSuccess)                                                                                    \
+            return fgp::fail(m, FGP_ERR_COMM, std::string(#call) + ": " + nccl->GetErrorString(r__));              \
+    } while (0)
+
+// info holds 0 or the 1-based failing column of THIS rank; the first failure anywhere is the minimum over the non-zero ones
+static __global__ void info_encode_kernel(int* info, int decode) {
+    if (!decode) *info = (*info == 0) ? 0x7fffffff : *info;
+    else *info = (*info == 0x7fffffff) ? 0 : *info;
+}
+
+// owned block columns [c0, c1) (rows >= c0) -= B B^T restricted to them, B = packed panel buffer holding rows >= J*128
+static void update_from_buffer(fgp_model* m, const double* buf, int64_t J, int64_t Jend, int64_t c0, int64_t c1,
+                               const LaunchCtx& c, PotrfCounters* cnt) {
+    const int64_t rows = m->np - J * TILE;
+    GemmArgs g{};
+    g.C = m->L.p + c0 * TILE + c0 * TILE * m->cap; g.ldc = m->cap;
+    g.A = buf + (c0 - J) * TILE; g.lda = rows;
+    g.B = g.A; g.ldb = rows;
+    g.M = (int)(m->np - c0 * TILE); g.N = (int)((c1 - c0) * TILE); g.K = (int)((Jend - J) * TILE);
+    g.alpha = -1.0; g.beta_one = 1; g.lower = 1; g.k_from_tile = 0;
+    cnt->launches += gemm_nt_launch(g, c) > 0;
+}
+
+int factor_sharded(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& kt, double noise, int has_eps, double eps) {
+    fgp_comm* cm = m->comm;
+    const int P = cm->nranks, r = cm->rank;
+    const NcclApi* nccl = nccl_api();
+    if (P > 1 && !nccl) return fail(m, FGP_ERR_COMM, "libnccl.so.2 could not be loaded");
+    const int64_t np = m->np, nb = np / TILE, NP = (nb + PANEL_TILES - 1) / PANEL_TILES;
+    const int64_t W = (int64_t)PANEL_TILES * TILE;
+    CU(m, cm->pbuf[0].reserve((size_t)np * W));
+    CU(m, cm->pbuf[1].reserve((size_t)np * W));
+    CU(m, cudaMemsetAsync(m->info_d, 0, sizeof(int), m->st));
+    cm->bcast_bytes = 0.0;
+
+    // ---- Gram: only the block columns this rank owns (algebra/mod.rs:67-79 restricted to them) ---------------------
+    for (int64_t p = r; p < NP; p += P) {
+        const int64_t J = p * PANEL_TILES, Jend = std::min<int64_t>(J + PANEL_TILES, nb);
+        PairArgs pa{};
+        pa.xa_c = pa.xb_c = m->xc.p;
+        pa.xa_r = pa.xb_r = m->xr.p;
+        pa.na = pa.nb = m->nc.p;
+        pa.dp = (int)m->dp;
+        pa.rows = pa.cols = np;
+        pa.row_tile0 = (int)J;
+        pa.col_tile0 = (int)(J * TILE / PAIR_TN);
+        pa.col_tiles = (int)((Jend - J) * TILE / PAIR_TN);
+        pa.symmetric = 1;
+        write_covariance(m, kt, kd, pa, m->L.p, m->cap, m->n, m->n, noise * noise);
+    }
+
+    const LaunchCtx mc = m->ctx();
+    LaunchCtx pc = mc;
+    pc.st = m->st2;
+    PotrfCounters cnt;
+    CU(m, cudaEventRecord(m->evA, m->st));
+    CU(m, cudaStreamWaitEvent(m->st2, m->evA, 0));
+    for (int64_t p = 0; p < NP; ++p) {
+        const int64_t J = p * PANEL_TILES, Jend = std::min<int64_t>(J + PANEL_TILES, nb);
+        const int64_t rows = np - J * TILE, w = (Jend - J) * TILE;
+        const int owner = shard_owner(p, P);
+        double* buf = cm->pbuf[p & 1].p;
+        if (p >= 2) CU(m, cudaStreamWaitEvent(m->st2, cm->ev_trail[p & 1], 0));
+        if (owner == r) {
+            if (p >= 1) {
+                const int64_t Jp = (p - 1) * PANEL_TILES;
+                update_from_buffer(m, cm->pbuf[(p - 1) & 1].p, Jp, J, J, Jend, pc, &cnt);
+            }
+            factor_panel(m->L.p, m->cap, np, J, Jend, m->inv.p, m->invT.p, has_eps, eps, m->info_d, pc, &cnt);
+            CU(m, cudaMemcpy2DAsync(buf, rows * sizeof(double), m->L.p + J * TILE + J * TILE * m->cap,
+                                    m->cap * sizeof(double), rows * sizeof(double), w, cudaMemcpyDeviceToDevice, m->st2));
+        }
+        if (P > 1) {
+            NC(m, nccl->Broadcast(buf, buf, (size_t)rows * w, ncclDouble, owner, cm->comm, m->st2));
+            cm->bcast_bytes += (double)rows * w * sizeof(double);
+        }
+        CU(m, cudaEventRecord(cm->ev_bcast, m->st2));
+        CU(m, cudaStreamWaitEvent(m->st, cm->ev_bcast, 0));
+        {
+            // every owned panel c > p, c != p+1 (that one is the owner's look-ahead on the panel stream next iteration),
+            // in ONE launch: the owned panels are groups of PANEL_TILES tile columns, P*PANEL_TILES tile columns apart
+            int64_t c_first = p + 1 + ((r - (p + 1)) % P + P) % P;
+            if (c_first == p + 1) c_first += P;
+            if (c_first < NP) {
+                const int64_t c0 = c_first * PANEL_TILES;
+                int64_t ncols = 0;
+                for (int64_t c = c_first; c < NP; c += P) ncols += std::min<int64_t>(PANEL_TILES, nb - c * PANEL_TILES);
+                GemmArgs g{};
+                g.C = m->L.p + c0 * TILE + c0 * TILE * m->cap; g.ldc = m->cap;
+                g.A = buf + (c0 - J) * TILE; g.lda = rows;
+                g.B = g.A; g.ldb = rows;
+                g.M = (int)(np - c0 * TILE); g.N = (int)(ncols * TILE); g.K = (int)w;
+                g.alpha = -1.0; g.beta_one = 1; g.lower = 1; g.k_from_tile = 0;
+                g.grp = PANEL_TILES; g.stride = P * PANEL_TILES;
+                cnt.launches += gemm_nt_launch(g, mc) > 0;
+            }
+        }
+        if (owner != r)
+            CU(m, cudaMemcpy2DAsync(m->L.p + J * TILE + J * TILE * m->cap, m->cap * sizeof(double), buf,
+                                    rows * sizeof(double), rows * sizeof(double), w, cudaMemcpyDeviceToDevice, m->st));
+        CU(m, cudaEventRecord(cm->ev_trail[p & 1], m->st));
+    }
+    // the inverted diagonal tiles live with their owners; every rank needs them for the triangular solves that follow
+    if (P > 1) {
+        CU(m, cudaStreamWaitEvent(m->st2, cm->ev_trail[(NP - 1) & 1], 0));
+        NC(m, nccl->GroupStart());
+        for (int64_t p = 0; p < NP; ++p) {
+            const int64_t J = p * PANEL_TILES, Jend = std::min<int64_t>(J + PANEL_TILES, nb);
+            const size_t cnt_d = (size_t)(Jend - J) * TILE * TILE;
+            NC(m, nccl->Broadcast(m->inv.p + J * TILE * TILE, m->inv.p + J * TILE * TILE, cnt_d, ncclDouble, shard_owner(p, P),
+                                cm->comm, m->st2));
+            NC(m, nccl->Broadcast(m->invT.p + J * TILE * TILE, m->invT.p + J * TILE * TILE, cnt_d, ncclDouble,
+                                shard_owner(p, P), cm->comm, m->st2));
+        }
+        NC(m, nccl->GroupEnd());
+        info_encode_kernel<<<1, 1, 0, m->st2>>>(m->info_d, 0);
+        NC(m, nccl->AllReduce(m->info_d, m->info_d, 1, ncclInt, ncclMin, cm->comm, m->st2));  // first failing column anywhere
+        info_encode_kernel<<<1, 1, 0, m->st2>>>(m->info_d, 1);
+        CU(m, cudaEventRecord(cm->ev_bcast, m->st2));
+        CU(m, cudaStreamWaitEvent(m->st, cm->ev_bcast, 0));
+    }
+    m->launches += cnt.launches;
+    return FGP_OK;
+}
+
+}  // namespace fgp

@@ -1,0 +1,29 @@
+// sharded.cuh — multi-GPU (one process per GPU) block-column Cholesky: 1-D block-cyclic ownership of the 512-wide
+// panels, NCCL broadcast of each factored panel over NVLink, one-panel look-ahead.  The reference has
+// no counterpart (single-threaded crate); the entry points are declared in include/fgp.h (fgp_comm_*, fgp_fit_sharded).
+#pragma once
+
+#include "nccl_dyn.cuh"
+
+#include "kernel_eval.cuh"
+#include "model.cuh"
+#include "potrf.cuh"
+
+struct fgp_comm {
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+    fgp::DevBuf pbuf[2];                     // contiguous panel buffers: rows [J*128, np) x panel width, ld = rows
+    cudaEvent_t ev_bcast = nullptr;          // panel J has arrived (recorded on the panel stream)
+    cudaEvent_t ev_trail[2] = {nullptr, nullptr};  // trailing update with panel J done (main stream), index J & 1
+    double bcast_bytes = 0.0;                // bytes this rank sent or received in the last sharded factorisation
+};
+
+namespace fgp {
+
+// panel p (PANEL_TILES block columns) is owned by rank p % nranks
+inline int shard_owner(int64_t panel, int nranks) { return (int)(panel % nranks); }
+
+// Gram assembly of the owned panels + the sharded factorisation; on return every rank holds the complete factor in m->L.
+int factor_sharded(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& kt, double noise, int has_eps, double eps);
+
+}  // namespace fgp

@@ -112,6 +112,29 @@ int fgp_download_alpha(fgp_model* m, double* alpha);
  * column-major (lower triangle read) and is overwritten by L with the strict upper triangle zeroed. */
 int fgp_cholesky_lower(int device, double* A, int64_t lda, int64_t n, int64_t* failed_col);
 
+/* multi-GPU fit (no reference counterpart: the crate is single-threaded) ---------------------------
+ * One process per GPU.  The 512-column panels of the covariance matrix are owned block-cyclically; each rank assembles
+ * only its own panels (algebra/mod.rs:70-79 restricted to them), the owner of a panel factors it and ncclBroadcast()s it
+ * over NVLink, every rank applies it to the panels it owns (one-panel look-ahead).  When the call returns EVERY rank
+ * holds the complete factor and alpha, so predict / likelihood / lml_gradient run locally (queries shard trivially).
+ * fgp_comm_unique_id   rank 0: ncclGetUniqueId into a caller buffer of FGP_COMM_ID_BYTES bytes; the caller ships it to
+ *                      the other processes (bench.py: torch.distributed broadcast — plumbing only).
+ * fgp_comm_init_rank   every rank: ncclCommInitRank on the handle's GPU.  nranks == 1 needs no id exchange.
+ * fgp_fit_sharded      fgp_fit, collectively. X / y_resid are read on rank 0 (others may pass NULL) and broadcast.
+ * fgp_refit_sharded    fgp_refit, collectively (inputs already resident on every rank).
+ * fgp_shard_plan       host-only: panel width, panel count, panels owned by `rank`, its share of the update flops.
+ * fgp_comm_last_bytes  bytes this rank sent or received in panel broadcasts during the last sharded factorisation. */
+#define FGP_COMM_ID_BYTES 128
+int fgp_comm_unique_id(void* id_out, size_t bytes);
+int fgp_comm_init_rank(fgp_model* m, const void* id, size_t bytes, int nranks, int rank);
+int fgp_comm_destroy(fgp_model* m);
+int fgp_fit_sharded(fgp_model* m, const double* X, int64_t ldx, int64_t n, int64_t d, const double* y_resid,
+                    const fgp_kernel_desc* kernel, double noise, int has_eps, double eps);
+int fgp_refit_sharded(fgp_model* m, const fgp_kernel_desc* kernel, double noise, int has_eps, double eps);
+int fgp_shard_plan(int64_t n, int nranks, int rank, int64_t* panel_cols, int64_t* n_panels, int64_t* n_owned,
+                   double* flop_share);
+double fgp_comm_last_bytes(const fgp_model* m);
+
 /* measurement --------------------------------------------------------------------------------------------------
  * Device time (CUDA events on the model's stream) and number of kernel launches of the last entry-point call. */
 double fgp_last_device_ms(const fgp_model* m);
@@ -138,6 +161,10 @@ void fgp_free_pinned(void* p);
 /* test hook: C = beta*C + alpha*A*B^T on device copies of host matrices, through the production GEMM kernel */
 int fgp_dbg_gemm_nt(int device, double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb,
                     int M, int N, int K, double alpha, int beta_one, int lower);
+
+/* test hook, host only: the (tile row, tile column) each thread block of a lower-mode GEMM launch computes, for M x N
+ * extents and tile-column groups of `grp` columns `stride` apart (the sharded trailing update); returns the tile count. */
+int64_t fgp_dbg_lower_tiles(int M, int N, int grp, int stride, int* ti_out, int* tj_out, int64_t capacity);
 
 #ifdef __cplusplus
 }

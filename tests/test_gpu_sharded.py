@@ -1,0 +1,74 @@
+"""GPU tests of the sharded (multi-GPU) fit entry points on ONE GPU: a communicator of size 1 runs the very same
+schedule (owned-panel Gram assembly, pack, look-ahead update from the packed panel buffer, unpack) without NCCL traffic.
+The 2/4/8-GPU runs are checked by tools/sharded_check.py (under torchrun; results in profiles/)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    from friedrich_b200 import _native as N
+    from friedrich_b200 import sharded
+    from friedrich_b200.kernels import Matern2, SquaredExp
+    from friedrich_b200.synthetic import make_dataset
+    from oracle import oracle as O
+    return N, sharded, SquaredExp, Matern2, make_dataset, O
+
+
+def _factor(N, h, n):
+    L = np.zeros((n, n), order="F")
+    h.check(N.lib().fgp_download_factor(h.ptr, N.dptr(L), n))
+    return L
+
+
+@pytest.mark.parametrize("n,d", [(100, 2), (640, 3), (1500, 8), (2049, 5)])
+def test_single_rank_sharded_fit_matches_oracle_and_plain_fit(n, d):
+    N, sharded, SquaredExp, Matern2, make_dataset, O = _mods()
+    X, y = make_dataset(4000 + n, n, d)
+    ls = math.sqrt(d / 6.0)
+    kd = SquaredExp(ls, 1.0).device_desc()
+    hs, hp = N.Handle(0), N.Handle(0)
+    sharded.comm_init(hs, 0, 1)
+    sharded.fit_sharded(hs, X, y, kd, 0.1)
+    hp.check(N.lib().fgp_fit(hp.ptr, N.dptr(N.fcol(X)), n, n, d, N.dptr(y), C.byref(kd), 0.1, 0, 0.0))
+    Ls, Lp = _factor(N, hs, n), _factor(N, hp, n)
+    # every tile sees the same operands in the same order whichever schedule applies the update => bitwise equal
+    assert np.array_equal(np.tril(Ls), np.tril(Lp))
+    ref = O.OracleGaussianProcess(O.ZeroPrior(), O.KernelDesc.make([O.K_SQUARED_EXP], [ls, 1.0]), 0.1, None, X, y)
+    err = np.linalg.norm(np.tril(Ls) - np.tril(ref.L)) / np.linalg.norm(np.tril(ref.L))
+    assert err < 1e-10
+    a_s, a_p = np.zeros(n), np.zeros(n)
+    hs.check(N.lib().fgp_download_alpha(hs.ptr, N.dptr(a_s)))
+    hp.check(N.lib().fgp_download_alpha(hp.ptr, N.dptr(a_p)))
+    assert np.array_equal(a_s, a_p)
+    # refit with another kernel through the collective entry point
+    kd2 = Matern2(ls, 1.3).device_desc()
+    sharded.refit_sharded(hs, kd2, 0.2)
+    hp.check(N.lib().fgp_refit(hp.ptr, C.byref(kd2), 0.2, 0, 0.0))
+    assert np.array_equal(np.tril(_factor(N, hs, n)), np.tril(_factor(N, hp, n)))
+
+
+def test_sharded_fit_reports_failing_column():
+    N, sharded, SquaredExp, Matern2, make_dataset, O = _mods()
+    n, d = 700, 2
+    X, y = make_dataset(77, n, d)
+    X[650] = X[3]  # duplicate point + zero noise => singular covariance
+    kd = SquaredExp(0.5, 1.0).device_desc()
+    h = N.Handle(0)
+    sharded.comm_init(h, 0, 1)
+    with pytest.raises(N.NotPositiveDefinite):
+        sharded.fit_sharded(h, X, y, kd, 0.0)
+    assert 0 <= N.lib().fgp_failed_column(h.ptr) <= 650
+
+
+def test_sharded_fit_without_communicator_is_an_error():
+    N, sharded, SquaredExp, Matern2, make_dataset, O = _mods()
+    X, y = make_dataset(5, 64, 2)
+    h = N.Handle(0)
+    with pytest.raises(N.FgpError) as e:
+        sharded.fit_sharded(h, X, y, SquaredExp(1.0, 1.0).device_desc(), 0.1)
+    assert e.value.code == N.FGP_ERR_COMM

@@ -1,0 +1,86 @@
+"""CPU tests of the multi-GPU host logic: the block-cyclic plan exported by the library (host-only entry point) and the
+world_size-2 gloo plumbing that ships the NCCL id between processes.  No GPU, no compute calls."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from friedrich_b200 import sharded
+
+
+@pytest.mark.parametrize("n", [100, 512, 4096, 16384, 32768, 33000])
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_plan_partitions_every_panel_exactly_once(n, world):
+    plans = [sharded.shard_plan(n, world, r) for r in range(world)]
+    n_panels = plans[0]["n_panels"]
+    assert plans[0]["panel_cols"] == 512
+    assert n_panels == -(-(-(-n // 128)) // 4)  # ceil(ceil(n/128)/4)
+    owned = sorted(p for pl in plans for p in pl["owned"])
+    assert owned == list(range(n_panels))
+    assert sum(pl["n_owned"] for pl in plans) == n_panels
+    assert abs(sum(pl["flop_share"] for pl in plans) - 1.0) < 1e-12
+    if n >= 16384:  # block-cyclic keeps the trailing-update work balanced for the sizes the configs use
+        assert max(pl["flop_share"] for pl in plans) < 1.0 / world + (0.07 if world <= 4 else 0.06)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        uid = sharded.exchange_id(dist, rank, lambda: bytes(range(128)))
+        plan = sharded.shard_plan(32768, world, rank)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, plan["owned"])
+        np.save(os.path.join(out_dir, f"r{rank}.npy"), np.array([len(uid), uid[5], sum(len(g) for g in gathered),
+                                                                    len(set(p for g in gathered for p in g))]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_id_exchange_and_plan_agreement(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        got = np.load(tmp_path / f"r{r}.npy")
+        assert got[0] == 128 and got[1] == 5      # both ranks hold rank 0's id bytes
+        assert got[2] == 64 and got[3] == 64      # 64 panels at n=32768, each owned exactly once across the ranks
+
+
+def test_sharded_entry_points_fail_loudly_without_gpu():
+    import ctypes as C
+    from friedrich_b200 import _native as N
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = N._h()
+    assert N.lib().fgp_create(0, C.byref(h)) == N.FGP_ERR_CUDA  # no device => no handle => no sharded fit, no fallback
+
+
+@pytest.mark.parametrize("tm,tn,grp,stride", [(1, 1, 1, 1), (7, 7, 1, 1), (9, 4, 1, 1), (128, 128, 1, 1), (20, 8, 4, 4),
+                                              (64, 16, 4, 8), (61, 15, 4, 16), (250, 32, 4, 32), (33, 9, 4, 12)])
+def test_lower_mode_block_to_tile_map_is_exact(tm, tn, grp, stride):
+    """Every thread block of a (sharded) trailing-update launch must land on a distinct tile on or below the diagonal of
+    exactly the owned tile columns — checked on the host copy of the device decode."""
+    import ctypes as C
+    from friedrich_b200 import _native as N
+    expect = []
+    for jl in range(tn):
+        tj = (jl // grp) * stride + jl % grp
+        expect += [(ti, tj) for ti in range(tj, tm)]
+    cap = len(expect) + 8
+    ti, tj = (C.c_int * cap)(), (C.c_int * cap)()
+    tiles = N.lib().fgp_dbg_lower_tiles(tm * 128, tn * 128, grp, stride, ti, tj, cap)
+    assert tiles == len(expect)
+    assert [(ti[b], tj[b]) for b in range(tiles)] == expect
