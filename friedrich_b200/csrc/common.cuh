@@ -125,6 +125,17 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                  : "memory");
 }
 
+// global -> shared 2-D tile through the TMA engine (cp.async.bulk.tensor -> SASS UTMALDG): the box described by the tensor
+// map at coordinates (c0 = index along the contiguous dimension, c1 = column); out-of-range elements arrive as zeros and
+// the mbarrier is always credited with the full box size
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
 // asynchronous L2 prefetch of `bytes` (multiple of 16) starting at a 16-byte aligned global address
 __device__ __forceinline__ void l2_prefetch(const void* gmem, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem), "r"(bytes) : "memory");

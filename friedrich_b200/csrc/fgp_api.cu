@@ -840,18 +840,61 @@ FGP_EXPORT int fgp_refit_sharded(fgp_model* m, const fgp_kernel_desc* kernel, do
 }
 
 // =================================================================================================================
-// test hook (host only, no GPU): the block -> tile map of the lower-mode GEMM launches, see lower_tile_decode
+// test hook (host only, no GPU): the block -> tile map of the lower-mode GEMM launches, see gemm_tile_decode
 FGP_EXPORT int64_t fgp_dbg_lower_tiles(int M, int N, int grp, int stride, int* ti_out, int* tj_out, int64_t capacity) {
     GemmArgs g{};
     g.M = M; g.N = N; g.K = GEMM_KC; g.lower = 1; g.grp = grp; g.stride = stride;
     const int64_t tiles = gemm_nt_tiles(g);
-    for (int64_t b = 0; b < tiles && b < capacity; ++b)
-        lower_tile_decode(M / GEMM_BM, std::max(grp, 1), std::max(stride, 1), (int)b, ti_out[b], tj_out[b]);
+    gemm_nt_plan(g);
+    for (int64_t b = 0; b < tiles && b < capacity; ++b) gemm_tile_decode(g, (int)b, ti_out[b], tj_out[b]);
     return tiles;
 }
 
 // =================================================================================================================
 // test hook: the production GEMM on host matrices
+FGP_EXPORT int fgp_dbg_gemm_occupancy(int device) {
+    DeviceGuard dg(device);
+    return gemm_nt_occupancy();
+}
+
+FGP_EXPORT int fgp_dbg_gemm_bench(int device, int M, int N, int K, int lower, int beta_one, int reps, double* ms_out,
+                                  double* flops_out) {
+    if (M % GEMM_BM || N % GEMM_BN || K % GEMM_KC || reps < 1 || !ms_out) return FGP_ERR_BAD_ARG;
+    DeviceGuard dg(device);
+    if (gemm_nt_prepare() != cudaSuccess) return FGP_ERR_CUDA;
+    double *dC = nullptr, *dA = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = FGP_OK;
+    if (cudaMalloc(&dC, (size_t)M * N * 8) != cudaSuccess || cudaMalloc(&dA, (size_t)M * K * 8) != cudaSuccess ||
+        cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)
+        rc = FGP_ERR_CUDA;
+    if (rc == FGP_OK) {
+        cudaMemset(dC, 0, (size_t)M * N * 8);
+        cudaMemset(dA, 0, (size_t)M * K * 8);
+        GemmArgs g{};
+        g.C = dC; g.ldc = M;
+        g.A = dA; g.lda = M;
+        g.B = dA; g.ldb = M;  // SYRK-shaped: B = the first N rows of A
+        g.M = M; g.N = N; g.K = K;
+        g.alpha = -1.0; g.beta_one = beta_one; g.lower = lower; g.k_from_tile = 0;
+        gemm_nt_launch(g, LaunchCtx{});  // warm-up
+        cudaEventRecord(e0, nullptr);
+        for (int r = 0; r < reps; ++r) gemm_nt_launch(g, LaunchCtx{});
+        cudaEventRecord(e1, nullptr);
+        if (cudaEventSynchronize(e1) != cudaSuccess) rc = FGP_ERR_CUDA;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *ms_out = ms / reps;
+        if (flops_out) *flops_out = gemm_nt_flops(g);
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(dC);
+    cudaFree(dA);
+    if (cudaGetLastError() != cudaSuccess) rc = FGP_ERR_CUDA;
+    return rc;
+}
+
 FGP_EXPORT int fgp_dbg_gemm_nt(int device, double* C, int64_t ldc, const double* A, int64_t lda, const double* B,
                                int64_t ldb, int M, int N, int K, double alpha, int beta_one, int lower) {
     if (M % GEMM_BM || N % GEMM_BN || K % GEMM_KC) return FGP_ERR_BAD_ARG;

@@ -7,13 +7,24 @@
 // axpy chain of nalgebra's Cholesky::new_internal, called at src/algebra/mod.rs:83,90), the panel solve
 // L21 = A21 * inv(L11)^T, the multi-RHS forward solve on the transposed right-hand side, U = L^-T and K^-1 = U U^T.
 //
-// Execution model (one CTA per 128x128 output tile, 288 threads):
-//   * warp 8  = producer: per k-chunk of 16 columns it arms an mbarrier and issues 32 TMA bulk copies (UBLKCP),
-//     one 1 KiB column segment per lane, into a 4-stage shared-memory ring. Columns are laid out [k][132] doubles;
-//     the 4-double pad makes the DMMA fragment reads (8 rows x 4 k per instruction) bank-conflict free.
-//   * warps 0-7 = consumers: each owns a 32x64 sub-tile = 4x8 DMMA.8x8x4 accumulators (128 registers), waits on the
-//     stage's "full" mbarrier, runs 4 k-steps x 32 DMMA, releases the stage on its "empty" mbarrier.
-//   * epilogue: accumulators are combined with C in global memory (each lane group writes 64-byte column runs).
+// Execution model (persistent CTAs of 128 threads, two resident per SM; a CTA computes 64 x 128 half tiles — the two row
+// halves of a 128x128 tile are consecutive work items; 8 warps per SM is the most the register file allows at 128
+// accumulator registers per thread: 16 K registers per SM sub-partition / 2 warps):
+//   * every warp owns a 32x64 sub-tile = 4x8 DMMA.8x8x4 accumulators (128 registers); per k-chunk of 16 columns it waits on
+//     the stage's "full" mbarrier, runs 4 k-steps x 32 DMMA, and releases the stage on its "empty" mbarrier;
+//   * there is no producer warp: the warps take turns (chunk index mod 4) refilling the 4-stage shared-memory ring two
+//     chunks ahead — wait for the stage's "empty" barrier, arm "full", and one lane issues two TMA tensor copies (UTMALDG):
+//     a (64+4) x 16 box of A and a (128+4) x 16 box of B. The 4 extra rows per column are never read: they ARE the padding
+//     that makes the shared-memory column stride 68 / 132 doubles, which keeps the DMMA fragment reads (8 rows x 4 k per
+//     instruction) bank-conflict free. (Per-lane 1-D bulk copies, one column each, cost 7 % of the kernel: the 32 UBLKCP
+//     of a chunk are serialised through uniform registers.) The ring runs ACROSS work items when a CTA has several;
+//   * epilogue: accumulators are combined with C in global memory (each lane group writes 64-byte column runs); the C
+//     tile was prefetched into L2 when its first operand chunk was requested. While one CTA of the SM is in its epilogue
+//     the other keeps the DMMA pipe busy;
+//   * lower-mode launches walk the triangle in bands of GEMM band rows (tile rows), column by column inside a band, so
+//     that the A blocks of a band stay L2-resident while the B blocks stream (gemm_nt_plan / gemm_tile_decode).
+//   Splitting the tile by ROWS keeps the in-place products (C aliases A: panel solve, multi-RHS solve) race free: a CTA
+//   only ever reads the rows of A it later overwrites.
 //
 // All extents are multiples of the tile (matrices are padded), so there is no edge code.
 #pragma once
@@ -22,11 +33,16 @@
 
 namespace fgp {
 
-constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_KC = 16, GEMM_STAGES = 4;
-constexpr int GEMM_LDS = GEMM_BM + 4;                                   // 132: smem column stride in doubles
-constexpr int GEMM_STAGE_DOUBLES = 2 * GEMM_KC * GEMM_LDS;              // A + B tile of one stage
+constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_KC = 16, GEMM_STAGES = 4;  // BM x BN: the tile the launch grid counts
+constexpr int GEMM_CTA_M = 64;                                          // rows of the tile one CTA computes
+constexpr int GEMM_LDA = GEMM_CTA_M + 4;                                // 68: smem column stride of the A stage (doubles)
+constexpr int GEMM_LDB = GEMM_BN + 4;                                   // 132: smem column stride of the B stage
+constexpr int GEMM_STAGE_DOUBLES = GEMM_KC * (GEMM_LDA + GEMM_LDB);     // A + B tile of one stage
 constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_DOUBLES * 8 + 2 * GEMM_STAGES * 8;
-constexpr int GEMM_THREADS = 288;
+constexpr int GEMM_WARPS = 4;
+constexpr int GEMM_AHEAD = 2;                                           // k-chunks in flight ahead of the one consumed
+constexpr int GEMM_THREADS = 32 * GEMM_WARPS;
+constexpr int GEMM_MAX_BANDS = 64, GEMM_BAND_ROWS = 16;
 
 struct GemmArgs {
     double* C;
@@ -44,36 +60,55 @@ struct GemmArgs {
                      //    are `stride` tile columns apart (0,0 = contiguous); rows/columns are relative to C, whose origin
                      //    is on the diagonal
     int k_from_tile; // 1: contraction starts at k = 128*max(tile_row, tile_col) (operands upper-triangular: U U^T)
+    // filled by gemm_nt_plan (called by gemm_nt_launch): the band rasterisation of lower-mode launches
+    int band_rows;                          // tile rows per band
+    int n_bands;
+    int band_prefix[GEMM_MAX_BANDS + 1];    // tiles in bands 0 .. r-1
 };
 
-// Lower mode: linear block index b -> tile (ti, tj), both relative to C (whose origin is on the diagonal).
-// Tile columns come in groups of PT consecutive columns, group q starting at tile column q*S (S = PT: the plain triangle /
-// trapezoid; S = P*PT: the panels one rank owns under the block-cyclic distribution).  Column tj holds the (tm - tj) tiles
-// on or below the diagonal; blocks enumerate them column by column.
-__host__ __device__ inline void lower_tile_decode(int tm, int PT, int S, int b, int& ti, int& tj) {
-    const double a = (double)PT * tm - 0.5 * PT * (PT - 1), c2 = 0.5 * S * PT;
-    const double disc = (a + c2) * (a + c2) - 4.0 * c2 * (double)b;
-    int gi = (int)(((a + c2) - sqrt(disc > 0.0 ? disc : 0.0)) / (2.0 * c2));
-    if (gi < 0) gi = 0;
-    auto prefix = [&](int q) -> int64_t {  // tiles in groups 0 .. q-1
-        return (int64_t)q * PT * tm - (int64_t)q * (PT * (PT - 1) / 2) - (int64_t)S * PT * ((int64_t)q * (q - 1) / 2);
-    };
-    while (gi > 0 && prefix(gi) > b) --gi;
-    while (tm - (int64_t)(gi + 1) * S > 0 && prefix(gi + 1) <= b) ++gi;
-    int rem = b - (int)prefix(gi);
-    int w = 0;
-    for (; w < PT - 1; ++w) {
-        const int cnt = tm - gi * S - w;
-        if (rem < cnt) break;
-        rem -= cnt;
+// Lower mode: the tiles of the launch, relative to C (whose origin is on the diagonal): local tile column jl sits at tile
+// column tj = (jl / PT) * S + jl % PT (groups of PT consecutive columns, group q starting at tile column q*S; S = PT: the
+// plain triangle / trapezoid; S = P*PT: the panels one rank owns under the block-cyclic distribution) and holds the tiles
+// ti = tj .. tm-1.  They are enumerated band by band (band r = tile rows [r*R, (r+1)*R)), inside a band column by column,
+// inside a column top to bottom.  gemm_tile_decode maps the linear tile index to (ti, tj) using the per-band prefix counts.
+__host__ __device__ inline void gemm_tile_decode(const GemmArgs& g, int b, int& ti, int& tj) {
+    const int tm = g.M / GEMM_BM;
+    if (!g.lower) {
+        ti = b % tm;
+        tj = b / tm;
+        return;
     }
-    tj = gi * S + w;
-    ti = tj + rem;
+    const int PT = g.grp > 0 ? g.grp : 1, S = g.stride > 0 ? g.stride : 1, tn = g.N / GEMM_BN, R = g.band_rows;
+    int r = 0;
+    while (r + 1 < g.n_bands && g.band_prefix[r + 1] <= b) ++r;
+    int o = b - g.band_prefix[r];
+    const int lo = r * R, hi = (lo + R < tm) ? lo + R : tm, h = hi - lo;
+    // local columns entirely above the band (tj < lo) are full-height
+    int nf = (lo / S) * PT + ((lo % S) < PT ? (lo % S) : PT);
+    if (nf > tn) nf = tn;
+    if (o < nf * h) {
+        const int jl = o / h;
+        tj = (jl / PT) * S + jl % PT;
+        ti = lo + o % h;
+        return;
+    }
+    o -= nf * h;
+    int jl = nf;
+    for (;; ++jl) {
+        tj = (jl / PT) * S + jl % PT;
+        const int cnt = hi - tj;
+        if (o < cnt) break;
+        o -= cnt;
+    }
+    ti = tj + o;
 }
 
 // defined in gemm_nt.cu
 int64_t gemm_nt_tiles(const GemmArgs& g);  // number of 128x128 tiles one launch computes
+void gemm_nt_plan(GemmArgs& g);             // fills band_rows / n_bands / band_prefix (host)
 cudaError_t gemm_nt_prepare();
+bool gemm_nt_take_error();  // true once after a launch could not be set up (tensor-map encode failure)
+int gemm_nt_occupancy();  // resident CTAs per SM of the GEMM kernel on the current device (2 by design), -1 on error
 // algorithmic flops of one launch (what the roofline figure in bench.py is computed from)
 double gemm_nt_flops(const GemmArgs& g);
 // launches nothing when the problem is empty; returns the number of tiles launched

@@ -162,6 +162,15 @@ void fgp_free_pinned(void* p);
 int fgp_dbg_gemm_nt(int device, double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb,
                     int M, int N, int K, double alpha, int beta_one, int lower);
 
+/* measurement hook: `reps` back-to-back launches of the production GEMM kernel on device-resident zero matrices, SYRK-shaped
+ * (C (M x N) -= A A[:N]^T, A is M x K; lower != 0: only tiles on/below the diagonal). *ms_out = CUDA-event time per launch,
+ * *flops_out = algorithmic flops per launch. Used by tools/gemm_bench.py for the kernel's isolated roofline figure. */
+int fgp_dbg_gemm_bench(int device, int M, int N, int K, int lower, int beta_one, int reps, double* ms_out, double* flops_out);
+
+/* test hook: resident CTAs per SM of the GEMM kernel on `device` (the design point is 2: one CTA's C read-modify-write
+ * overlaps the other's DMMA main loop); -1 on error */
+int fgp_dbg_gemm_occupancy(int device);
+
 /* test hook, host only: the (tile row, tile column) each thread block of a lower-mode GEMM launch computes, for M x N
  * extents and tile-column groups of `grp` columns `stride` apart (the sharded trailing update); returns the tile count. */
 int64_t fgp_dbg_lower_tiles(int M, int N, int grp, int stride, int* ti_out, int* tj_out, int64_t capacity);

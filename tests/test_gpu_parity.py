@@ -65,6 +65,12 @@ def test_gemm_nt_kernel_against_numpy(shape):
         assert np.allclose(out, ref, rtol=1e-12, atol=1e-12)
 
 
+def test_gemm_nt_kernel_runs_two_ctas_per_sm():
+    """Design point of gemm_nt.cu: two 64x128 CTAs resident per SM (one's epilogue overlaps the other's main loop)."""
+    F, N, O, *_ = _mods()
+    assert N.lib().fgp_dbg_gemm_occupancy(0) == 2
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def test_golden_anchors_on_gpu():
     """tests/golden/anchors.json (50-digit mpmath) through the device path."""
