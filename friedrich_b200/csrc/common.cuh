@@ -136,6 +136,24 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
         : "memory");
 }
 
+// shared -> global 2-D tile through the TMA engine (SASS UTMASTG / UTMAREDG), bulk-group completion:
+//   tma_store_2d   C[box] = smem            tma_reduce_add_2d   C[box] += smem  (element-wise f64 add performed at the L2)
+__device__ __forceinline__ void tma_store_2d(const void* tmap, int c0, int c1, const void* smem_src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(tmap), "r"(c0),
+                 "r"(c1), "r"(smem_u32(smem_src))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, int c0, int c1, const void* smem_src) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(tmap),
+                 "r"(c0), "r"(c1), "r"(smem_u32(smem_src))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+// the shared-memory source of every committed bulk group has been read (the CTA may exit / reuse the buffer)
+__device__ __forceinline__ void tma_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+// make this thread's generic-proxy shared-memory writes visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
 // asynchronous L2 prefetch of `bytes` (multiple of 16) starting at a 16-byte aligned global address
 __device__ __forceinline__ void l2_prefetch(const void* gmem, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem), "r"(bytes) : "memory");

@@ -3,7 +3,7 @@
 
 // Experiment switches for tools/microbench/gemm_variants.cu (the production build leaves FGP_GEMM_EXP at 0):
 //   1 = skip the epilogue (no C traffic)          2 = skip the operand loads and their barriers (main loop on stale smem)
-//   3 = both                                      4 = epilogue without the C read (beta = 0)
+//   3 = both
 #ifndef FGP_GEMM_EXP
 #define FGP_GEMM_EXP 0
 #endif
@@ -16,33 +16,22 @@
 
 namespace fgp {
 
-// One work item = one 64 x 128 half tile.
-struct HalfTile {
-    int m0, n0;      // origin in C
-    int kbeg, nk;    // first contraction index, number of 16-column chunks
-    int rbase;       // row of m0 inside its 128 x 128 tile (0 or 64)
-    bool diag;       // lower mode, tile on the diagonal
-};
-
-__device__ __forceinline__ HalfTile half_tile(const GemmArgs& g, int item) {
-    int ti, tj;
-    gemm_tile_decode(g, item >> 1, ti, tj);
-    HalfTile h;
-    h.rbase = (item & 1) * GEMM_CTA_M;
-    h.m0 = ti * GEMM_BM + h.rbase;
-    h.n0 = tj * GEMM_BN;
-    h.kbeg = g.k_from_tile ? GEMM_BM * max(ti, tj) : 0;
-    h.nk = (g.K - h.kbeg) / GEMM_KC;
-    h.diag = g.lower && (ti == tj);
-    return h;
-}
-
-__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_kernel(const __grid_constant__ GemmArgs g, int n_items, const __grid_constant__ CUtensorMap tmA,
-                                                                   const __grid_constant__ CUtensorMap tmB) {
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+gemm_nt_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ CUtensorMap tmA,
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* tiles = reinterpret_cast<double*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)GEMM_STAGES * GEMM_STAGE_DOUBLES * 8);
     uint64_t* empty = full + GEMM_STAGES;
+
+    // work item = one 64 x 128 half tile: block pair -> tile (ti, tj), block parity -> row half
+    int ti, tj;
+    gemm_tile_decode(g, blockIdx.x >> 1, ti, tj);
+    const int half = blockIdx.x & 1;
+    const int m0 = ti * GEMM_BM + half * GEMM_CTA_M, n0 = tj * GEMM_BN;
+    const int kbeg = g.k_from_tile ? GEMM_BM * max(ti, tj) : 0;
+    const int nk = (g.K - kbeg) / GEMM_KC;
+    const bool diag_tile = g.lower && (ti == tj);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -54,133 +43,97 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_kernel(const __grid_c
     }
     __syncthreads();
 
-    // ---------------- load cursor: runs GEMM_AHEAD chunks ahead of the compute cursor, across work items ----------------
-    // two TMA tensor copies per k-chunk, issued by one lane: a (64+4) x 16 box of A and a (128+4) x 16 box of B. The 4 extra
-    // rows are never read: they are the padding that makes the shared-memory column stride 68 / 132 doubles.
-    int l_item = blockIdx.x;   // work item the next load belongs to
-    int l_left = 0;            // chunks of that item not yet requested
-    int l_m0 = 0, l_n0 = 0, l_k = 0;
-    int l_idx = 0;             // running chunk index of the next load (stage = l_idx % STAGES)
-    auto load_enter = [&](int item) {  // position the cursor on the first chunk of `item`
-        const HalfTile h = half_tile(g, item);
-        l_left = h.nk;
-        l_m0 = h.m0;
-        l_n0 = h.n0;
-        l_k = h.kbeg;
-        // pull the C half tile (128 columns x 512 B) into L2 now so the epilogue's reads do not pay DRAM latency
-        if (g.beta_one) l2_prefetch(g.C + (int64_t)(h.n0 + lane + 32 * warp) * g.ldc + h.m0, GEMM_CTA_M * 8);
-    };
-    // every warp calls this once per chunk, in the same order; only `issuer` touches the barriers / TMA
-    auto load_step = [&](bool issuer) {
-        if (l_item >= n_items) return;
-        if (issuer && !(FGP_GEMM_EXP & 2)) {
-            const int s = l_idx % GEMM_STAGES;
-            if (l_idx >= GEMM_STAGES) mbar_wait(&empty[s], ((l_idx / GEMM_STAGES) + 1) & 1);
-            if (lane == 0) {
-                double* dst = tiles + (size_t)s * GEMM_STAGE_DOUBLES;
-                mbar_arrive_expect_tx(&full[s], GEMM_STAGE_DOUBLES * 8);
-                tma_load_2d(dst, &tmA, l_m0, l_k, &full[s]);
-                tma_load_2d(dst + GEMM_KC * GEMM_LDA, &tmB, l_n0, l_k, &full[s]);
-            }
-            __syncwarp();
+    // Operand chunk j -> stage j % STAGES: two TMA tensor copies issued by one lane, a (64+4) x 16 box of A and a (128+4) x 16
+    // box of B. The 4 extra rows are never read: they are the padding that makes the shared-memory column stride 68 / 132.
+    auto issue_load = [&](int j) {  // whole warp
+        if (FGP_GEMM_EXP & 2) return;
+        const int s = j % GEMM_STAGES;
+        if (j >= GEMM_STAGES) mbar_wait(&empty[s], ((j / GEMM_STAGES) + 1) & 1);  // chunk j - STAGES has left the stage
+        if (lane == 0) {
+            double* dst = tiles + (size_t)s * GEMM_STAGE_DOUBLES;
+            mbar_arrive_expect_tx(&full[s], GEMM_STAGE_DOUBLES * 8);
+            tma_load_2d(dst, &tmA, m0, kbeg + j * GEMM_KC, &full[s]);
+            tma_load_2d(dst + GEMM_KC * GEMM_LDA, &tmB, n0, kbeg + j * GEMM_KC, &full[s]);
         }
-        ++l_idx;
-        l_k += GEMM_KC;
-        if (--l_left == 0) {
-            l_item += gridDim.x;
-            if (l_item < n_items) load_enter(l_item);
-        }
+        __syncwarp();
     };
-    if (l_item < n_items) load_enter(l_item);
-#pragma unroll
-    for (int a = 0; a < GEMM_AHEAD; ++a) load_step(warp == a);
+    if (warp < GEMM_AHEAD && warp < nk) issue_load(warp);
+    // pull the C half tile (128 columns x 512 B) towards L2 now: the epilogue's read-modify-write happens there
+    if (g.beta_one) l2_prefetch(g.C + (int64_t)(n0 + lane + 32 * warp) * g.ldc + m0, GEMM_CTA_M * 8);
 
     const int gq = lane >> 2, t = lane & 3;
     const int wr = warp & 1, wc = warp >> 1;
-    int c_idx = 0;  // running chunk index of the compute cursor
+    // the top half of a diagonal tile has nothing on or below the diagonal in columns 64..127
+    const bool idle = diag_tile && half == 0 && wc == 1;
+    double acc[4][8][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const HalfTile h = half_tile(g, item);
-        // the top half of a diagonal tile has nothing on or below the diagonal in columns 64..127
-        const bool idle = h.diag && h.rbase == 0 && wc == 1;
-        double acc[4][8][2];
+    for (int it = 0; it < nk; ++it) {
+        // the warps take turns refilling the ring, GEMM_AHEAD chunks ahead of the one being consumed
+        if ((it & (GEMM_WARPS - 1)) == warp && it + GEMM_AHEAD < nk) issue_load(it + GEMM_AHEAD);
+        const int s = it % GEMM_STAGES;
+        if (!(FGP_GEMM_EXP & 2)) mbar_wait(&full[s], (it / GEMM_STAGES) & 1);
+        if (!idle) {
+            const double* As = tiles + (size_t)s * GEMM_STAGE_DOUBLES + t * GEMM_LDA + 32 * wr + gq;
+            const double* Bs = tiles + (size_t)s * GEMM_STAGE_DOUBLES + GEMM_KC * GEMM_LDA + t * GEMM_LDB + 64 * wc + gq;
+#pragma unroll
+            for (int kk = 0; kk < GEMM_KC / 4; ++kk) {
+                double fa[4], fb[8];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) fa[mi] = As[kk * 4 * GEMM_LDA + 8 * mi];
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni) fb[ni] = Bs[kk * 4 * GEMM_LDB + 8 * ni];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], fa[mi], fb[ni]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+    if (FGP_GEMM_EXP & 1) {  // keep the accumulators observable without any C traffic
+        double sum = 0.0;
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            for (int ni = 0; ni < 8; ++ni) sum += acc[mi][ni][0] + acc[mi][ni][1];
+        if (sum == 12345.678) g.C[0] = sum;
+        return;
+    }
 
-        for (int it = 0; it < h.nk; ++it, ++c_idx) {
-            // the warps take turns refilling the ring, GEMM_AHEAD chunks ahead of the one being consumed
-            load_step((c_idx & (GEMM_WARPS - 1)) == warp);
-            const int s = c_idx % GEMM_STAGES;
-            if (!(FGP_GEMM_EXP & 2)) mbar_wait(&full[s], (c_idx / GEMM_STAGES) & 1);
-            if (!idle) {
-                const double* As = tiles + (size_t)s * GEMM_STAGE_DOUBLES + t * GEMM_LDA + 32 * wr + gq;
-                const double* Bs = tiles + (size_t)s * GEMM_STAGE_DOUBLES + GEMM_KC * GEMM_LDA + t * GEMM_LDB + 64 * wc + gq;
-#pragma unroll
-                for (int kk = 0; kk < GEMM_KC / 4; ++kk) {
-                    double fa[4], fb[8];
-#pragma unroll
-                    for (int mi = 0; mi < 4; ++mi) fa[mi] = As[kk * 4 * GEMM_LDA + 8 * mi];
-#pragma unroll
-                    for (int ni = 0; ni < 8; ++ni) fb[ni] = Bs[kk * 4 * GEMM_LDB + 8 * ni];
-#pragma unroll
-                    for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                        for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], fa[mi], fb[ni]);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-        }
-        if (idle) continue;
-        if (FGP_GEMM_EXP & 1) {  // keep the accumulators observable without any C traffic
-            double sum = 0.0;
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 8; ++ni) sum += acc[mi][ni][0] + acc[mi][ni][1];
-            if (sum == 12345.678) g.C[0] = sum;
-            continue;
-        }
-
-        // ---------------- epilogue ----------------
-        // Two 8-column groups at a time: all 16 C values of the batch are loaded before any is used, so the loads of a
-        // batch are in flight together (the half tile was prefetched into L2 when its first chunk was requested).
+    // ---------------- epilogue ----------------
+    // alpha * acc is staged in the (now idle) operand ring as a dense 64 x 128 column-major image and handed to the TMA
+    // engine in ONE tensor operation: a reduce-add into C (beta = 1: the f64 addition happens at the L2, the SM never reads
+    // C) or a plain store (beta = 0). Elements above the diagonal of a diagonal tile are staged as zeros (C + 0 = C).
+    __syncthreads();  // every warp has consumed every chunk: no TMA write into the ring is pending, nobody reads it any more
+    {
         const double alpha = g.alpha;
-        const int rbase = h.rbase + 32 * wr + gq;  // row inside the 128x128 tile of this lane's mi = 0 element
-        double* cbase = g.C + (int64_t)h.n0 * g.ldc + h.m0 + 32 * wr + gq;
+        double* stage = tiles + 32 * wr + gq;
+        const int rbase = half * GEMM_CTA_M + 32 * wr + gq;  // row inside the 128x128 tile of this lane's mi = 0 element
 #pragma unroll
-        for (int nb2 = 0; nb2 < 4; ++nb2) {
-            double cv[2][2][4];
-            if (g.beta_one && FGP_GEMM_EXP != 4) {
+        for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh)
+            for (int e = 0; e < 2; ++e) {
+                const int cl = 64 * wc + 8 * ni + 2 * t + e;
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int cl = 64 * wc + 8 * (2 * nb2 + hh) + 2 * t + e;
-                        const double* cp = cbase + (int64_t)cl * g.ldc;
-#pragma unroll
-                        for (int mi = 0; mi < 4; ++mi) cv[hh][e][mi] = __ldcg(cp + 8 * mi);
-                    }
-            }
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int ni = 2 * nb2 + hh;
-                    const int cl = 64 * wc + 8 * ni + 2 * t + e;
-                    double* cp = cbase + (int64_t)cl * g.ldc;
-#pragma unroll
-                    for (int mi = 0; mi < 4; ++mi) {
-                        const int rl = rbase + 8 * mi;
-                        if (h.diag && rl < cl) continue;
-                        double v = alpha * acc[mi][ni][e];
-                        if (g.beta_one && FGP_GEMM_EXP != 4) v += cv[hh][e][mi];
-                        __stcg(cp + 8 * mi, v);
-                    }
+                for (int mi = 0; mi < 4; ++mi) {
+                    const bool above = diag_tile && (rbase + 8 * mi < cl);
+                    stage[cl * GEMM_CTA_M + 8 * mi] = (idle || above) ? 0.0 : alpha * acc[mi][ni][e];
                 }
-        }
+            }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (g.beta_one) tma_reduce_add_2d(&tmC, m0, n0, tiles);
+        else tma_store_2d(&tmC, m0, n0, tiles);
+        tma_commit_group();
+        tma_wait_group_read0();  // the staging image must outlive the TMA read
     }
 }
 
@@ -228,13 +181,14 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// rows x cols column-major f64 operand (leading dimension ld), box = box_rows x GEMM_KC
-static bool make_operand_map(CUtensorMap* tm, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// rows x cols column-major f64 matrix (leading dimension ld), box = box_rows x box_cols
+static bool make_operand_map(CUtensorMap* tm, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                             int box_cols = GEMM_KC) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
-    const cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)GEMM_KC};
+    const cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)box_cols};
     const cuuint32_t estr[2] = {1, 1};
     return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -307,19 +261,21 @@ int64_t gemm_nt_launch(const GemmArgs& g, const LaunchCtx& ctx) {
         if (g_num_sms <= 0) g_num_sms = 148;
     }
     const int64_t items = 2 * tiles;  // 64 x 128 half tiles
-    // one work item per CTA (the kernel also runs persistently with a smaller grid, but resident CTAs that never retire
-    // would starve the look-ahead stream's panel kernels, and measured no faster: DESIGN.md "GEMM")
+    // one work item per CTA (a persistent variant measured no faster and its never-retiring CTAs starve the look-ahead
+    // stream's panel kernels: DESIGN.md "GEMM")
     const unsigned grid = (unsigned)items;
     // operand extents: rows beyond them arrive as zeros (only the padding rows of the last tile ever are). In lower mode the
     // rows of B are addressed by tile COLUMN positions of C, which reach M when the owned columns are strided (sharded).
-    alignas(64) CUtensorMap tmA, tmB;
-    if (!make_operand_map(&tmA, g.A, g.M, g.K, g.lda, GEMM_LDA) || !make_operand_map(&tmB, g.B, g.lower ? g.M : g.N, g.K, g.ldb, GEMM_LDB)) {
+    alignas(64) CUtensorMap tmA, tmB, tmC;
+    const int64_t ncols = g.lower ? g.M : g.N;
+    if (!make_operand_map(&tmA, g.A, g.M, g.K, g.lda, GEMM_LDA) || !make_operand_map(&tmB, g.B, ncols, g.K, g.ldb, GEMM_LDB) ||
+        !make_operand_map(&tmC, g.C, g.M, ncols, g.ldc, GEMM_CTA_M, GEMM_BN)) {
         if (!g_gemm_error) fprintf(stderr, "libfgp_sm100: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)\n", g.M, g.N, g.K);
         g_gemm_error = true;
         return 0;
     }
     ProfScope ps(ctx, PROF_GEMM, gemm_nt_flops(g));
-    gemm_nt_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, ctx.st>>>(p, (int)items, tmA, tmB);
+    gemm_nt_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, ctx.st>>>(p, tmA, tmB, tmC);
     return tiles;
 }
 

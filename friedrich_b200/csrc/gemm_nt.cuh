@@ -7,9 +7,9 @@
 // axpy chain of nalgebra's Cholesky::new_internal, called at src/algebra/mod.rs:83,90), the panel solve
 // L21 = A21 * inv(L11)^T, the multi-RHS forward solve on the transposed right-hand side, U = L^-T and K^-1 = U U^T.
 //
-// Execution model (persistent CTAs of 128 threads, two resident per SM; a CTA computes 64 x 128 half tiles — the two row
-// halves of a 128x128 tile are consecutive work items; 8 warps per SM is the most the register file allows at 128
-// accumulator registers per thread: 16 K registers per SM sub-partition / 2 warps):
+// Execution model (CTAs of 128 threads, two resident per SM; a CTA computes one 64 x 128 half tile — the two row halves of a
+// 128x128 tile are consecutive blocks; 8 warps per SM is the most the register file allows at 128 accumulator registers
+// per thread: 16 K registers per SM sub-partition / 2 warps):
 //   * every warp owns a 32x64 sub-tile = 4x8 DMMA.8x8x4 accumulators (128 registers); per k-chunk of 16 columns it waits on
 //     the stage's "full" mbarrier, runs 4 k-steps x 32 DMMA, and releases the stage on its "empty" mbarrier;
 //   * there is no producer warp: the warps take turns (chunk index mod 4) refilling the 4-stage shared-memory ring two
@@ -17,14 +17,15 @@
 //     a (64+4) x 16 box of A and a (128+4) x 16 box of B. The 4 extra rows per column are never read: they ARE the padding
 //     that makes the shared-memory column stride 68 / 132 doubles, which keeps the DMMA fragment reads (8 rows x 4 k per
 //     instruction) bank-conflict free. (Per-lane 1-D bulk copies, one column each, cost 7 % of the kernel: the 32 UBLKCP
-//     of a chunk are serialised through uniform registers.) The ring runs ACROSS work items when a CTA has several;
-//   * epilogue: accumulators are combined with C in global memory (each lane group writes 64-byte column runs); the C
-//     tile was prefetched into L2 when its first operand chunk was requested. While one CTA of the SM is in its epilogue
-//     the other keeps the DMMA pipe busy;
+//     of a chunk are serialised through uniform registers.)
+//   * epilogue: alpha * acc is staged in the idle ring as a dense 64 x 128 image and leaves in ONE TMA tensor operation —
+//     a reduce-add into C (UTMAREDG; the f64 add is performed at the L2, the SM never reads C) or a plain store. While
+//     one CTA of the SM is in its prologue / epilogue the other keeps the DMMA pipe busy;
 //   * lower-mode launches walk the triangle in bands of GEMM band rows (tile rows), column by column inside a band, so
 //     that the A blocks of a band stay L2-resident while the B blocks stream (gemm_nt_plan / gemm_tile_decode).
 //   Splitting the tile by ROWS keeps the in-place products (C aliases A: panel solve, multi-RHS solve) race free: a CTA
-//   only ever reads the rows of A it later overwrites.
+//   only ever reads the rows of A it later overwrites. In lower mode the strict upper triangle of a diagonal tile is left
+//   unchanged by beta = 1 launches and zeroed by beta = 0 launches.
 //
 // All extents are multiples of the tile (matrices are padded), so there is no edge code.
 #pragma once
