@@ -39,8 +39,11 @@ potrf_diag_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ inv,
                         dk = nan("");
                     }
                 }
-                const double sk = sqrt(dk);
-                const double rs = 1.0 / sk;
+                // 1/sqrt first (one MUFU seed + Newton steps): the column scaling, which the next pivot waits for, needs
+                // only rs; sqrt(dk) = dk * rs gets one correction step off the critical path (<= 1 ulp)
+                const double rs = rsqrt(dk);
+                double sk = dk * rs;
+                sk = fma(0.5 * rs, fma(-sk, sk, dk), sk);
                 if (lane > k) row[k] *= rs;
                 else if (lane == k) { row[k] = sk; rdiag[c0 + k] = rs; }
                 if (lane >= k) Tr[k] = row[k];
