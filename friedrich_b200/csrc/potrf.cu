@@ -3,59 +3,240 @@
 
 namespace fgp {
 
-// One CTA: factor the 128x128 diagonal tile in shared memory (4 sub-panels of 32 columns: the 32x32 pivot block
-// is factored by one warp with the pivot row broadcast by shuffle), write L back, then invert L in place
-// (blocked dtrtri) and write the inverse (upper part zeroed) to `inv` (ld = 128).
-__global__ void __launch_bounds__(256, 1)
+// Phase timing hook for tools/microbench/diag_phases.cu (production builds leave FGP_DIAG_TIMING undefined)
+#ifdef FGP_DIAG_TIMING
+__device__ long long g_diag_clk[32];
+#define DIAG_MARK(i) do { if (threadIdx.x == 0) g_diag_clk[i] = clock64(); } while (0)
+#else
+#define DIAG_MARK(i) do { } while (0)
+#endif
+
+// 1/sqrt(x) for a positive, normal x without the library routine's special-case branches (they would split the pivot
+// chain into basic blocks): MUFU.RSQ64H seed (~2^-22) + one third-order step y (1 + e/2 + 3e^2/8), e = 1 - x y^2 -> <= 1 ulp.
+__device__ __forceinline__ double rsqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-(x * y), y, 1.0);
+    return fma(y * e, fma(0.375, e, 0.5), y);
+}
+
+// In-tile SYRK of the diagonal-tile factorisation: A[r][c] -= sum_k X[r][k] X[c][k] over the TN x TN block that follows
+// the 32-column sub-panel at column c0 (X = the sub-panel's rows below its pivot block). Register tiled: warp w owns rows
+// {w + 16 a}, lane l owns columns {l + 32 b}; row operands are warp-wide broadcasts, column operands are conflict free
+// (row stride 129). Pairs (a, b) entirely above the diagonal are skipped (warp-uniform test).
+template <int TN>
+__device__ __forceinline__ void diag_syrk(double* T, int c0, int warp, int lane) {
+    constexpr int NA = TN / 16, NB = TN / 32;
+    const int base = c0 + 32;
+    double acc[NA][NB];
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) acc[a][b] = 0.0;
+    const double* xr = T + (base + warp) * DIAG_DS + c0;
+    const double* xc = T + (base + lane) * DIAG_DS + c0;
+#pragma unroll 4
+    for (int k = 0; k < 32; ++k) {
+        double fr[NA], fc[NB];
+#pragma unroll
+        for (int a = 0; a < NA; ++a) fr[a] = xr[16 * a * DIAG_DS + k];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) fc[b] = xc[32 * b * DIAG_DS + k];
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+                if (warp + 16 * a + 1 > 32 * b) acc[a][b] = fma(fr[a], fc[b], acc[a][b]);
+    }
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int r = warp + 16 * a, c = lane + 32 * b;
+            if (r >= c) T[(base + r) * DIAG_DS + base + c] -= acc[a][b];
+        }
+}
+
+// ---- X = L^-1 of the diagonal tile, in 32-blocks.  X[r][c] (r > c) lives TRANSPOSED at T[c*DS + r] (the strict upper
+// triangle of T is otherwise unused), X[r][r] = rdiag[r].  Row block i:  X_ii = L_ii^-1,  X_ij = -X_ii S_j with
+// S_j = sum_{k=j}^{i-1} L_ik X_kj  (j < i).  It needs block row i of L and the row blocks < i of X, so row block s-1 is
+// computed by the otherwise idle warps WHILE warp 0 runs the pivot chain of sub-panel s; only row block 3 is exposed.
+// A 32x32 output block is split over 4 warps (8 rows each); lane (rg, cg) = (lane >> 3, lane & 7) owns rows
+// {rg, rg + 4} of the slice and columns {cg + 8 b}: per contraction index 2 + 4 shared-memory loads feed 8 FMAs.
+
+// X_ii by one warp: lane c owns column c of the block's inverse (forward substitution on e_c)
+__device__ __forceinline__ void diag_inv_block(double* T, const double* rdiag, int i, int lane) {
+    const int c0 = 32 * i;
+    double x[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) x[r] = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        x[r] *= rdiag[c0 + r];
+#pragma unroll
+        for (int r2 = r + 1; r2 < 32; ++r2) x[r2] = fma(-x[r], T[(c0 + r2) * DIAG_DS + c0 + r], x[r2]);
+    }
+#pragma unroll
+    for (int r = 0; r < 32; ++r)
+        if (r > lane) T[(c0 + lane) * DIAG_DS + c0 + r] = x[r];
+}
+
+// rows [8q, 8q+8) of S_j -> W[j][r][c]
+__device__ __forceinline__ void diag_inv_sum(const double* T, double* W, const double* rdiag, int i, int j, int q, int lane) {
+    const int rg = lane >> 3, cg = lane & 7;
+    double acc[2][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    const double* lrow = T + (32 * i + 8 * q + rg) * DIAG_DS;  // L[32 i + 8 q + rg (+4)][.]
+    const double* xcol = T + (32 * j + cg) * DIAG_DS;          // X[.][32 j + cg (+8 b)], transposed storage
+    // k = j: X_jj is lower triangular with its diagonal in rdiag
+#pragma unroll 4
+    for (int m = 0; m < 32; ++m) {
+        const double p0 = lrow[32 * j + m], p1 = lrow[4 * DIAG_DS + 32 * j + m];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int c = cg + 8 * b;
+            double xv = xcol[8 * b * DIAG_DS + 32 * j + m];
+            xv = (m > c) ? xv : ((m == c) ? rdiag[32 * j + c] : 0.0);
+            acc[0][b] = fma(p0, xv, acc[0][b]);
+            acc[1][b] = fma(p1, xv, acc[1][b]);
+        }
+    }
+    for (int k = j + 1; k < i; ++k) {
+#pragma unroll 4
+        for (int m = 0; m < 32; ++m) {
+            const double p0 = lrow[32 * k + m], p1 = lrow[4 * DIAG_DS + 32 * k + m];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const double xv = xcol[8 * b * DIAG_DS + 32 * k + m];
+                acc[0][b] = fma(p0, xv, acc[0][b]);
+                acc[1][b] = fma(p1, xv, acc[1][b]);
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) W[(j * 32 + 8 * q + rg + 4 * a) * 33 + cg + 8 * b] = acc[a][b];
+}
+
+// rows [8q, 8q+8) of X_ij = -X_ii S_j -> transposed storage
+__device__ __forceinline__ void diag_inv_apply(double* T, const double* W, const double* rdiag, int i, int j, int q, int lane) {
+    const int rg = lane >> 3, cg = lane & 7;
+    const int r0 = 8 * q + rg, r1 = r0 + 4;
+    double acc[2][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    const double* xi = T + 32 * i * DIAG_DS + 32 * i;  // X_ii[r][m] (m < r) at xi[m * DS + r]
+    const double* sb = W + j * 32 * 33 + cg;
+    const double d0 = rdiag[32 * i + r0], d1 = rdiag[32 * i + r1];
+#pragma unroll 4
+    for (int m = 0; m < 8 * q + 8; ++m) {  // X_ii[r][m] = 0 for m > r: rows of this slice end at 8q + 7
+        double p0 = xi[m * DIAG_DS + r0], p1 = xi[m * DIAG_DS + r1];
+        p0 = (m < r0) ? p0 : ((m == r0) ? d0 : 0.0);
+        p1 = (m < r1) ? p1 : ((m == r1) ? d1 : 0.0);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const double sv = sb[m * 33 + 8 * b];
+            acc[0][b] = fma(p0, sv, acc[0][b]);
+            acc[1][b] = fma(p1, sv, acc[1][b]);
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        T[(32 * j + cg + 8 * b) * DIAG_DS + 32 * i + r0] = -acc[0][b];
+        T[(32 * j + cg + 8 * b) * DIAG_DS + 32 * i + r1] = -acc[1][b];
+    }
+}
+
+// Row block i of X by the warp group gw = 0 .. ng-1 (ng >= 4 i + 1), synchronised on named barrier `bar_id`.
+__device__ __forceinline__ void diag_inv_rowblock(double* T, double* W, const double* rdiag, int i, int gw, int ng, int lane,
+                                                  int bar_id) {
+    if (gw == 0) diag_inv_block(T, rdiag, i, lane);
+    else if (gw <= 4 * i) diag_inv_sum(T, W, rdiag, i, (gw - 1) >> 2, (gw - 1) & 3, lane);
+    if (i == 0) return;
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * ng) : "memory");
+    if (gw < 4 * i) diag_inv_apply(T, W, rdiag, i, gw >> 2, gw & 3, lane);
+}
+
+// One CTA, 512 threads: factor the 128x128 diagonal tile in shared memory, write L back, invert it and write the inverse
+// and its transpose (`inv`, `invT`, ld = 128, other triangle zeroed).
+//   factorisation: 4 sub-panels of 32 columns — (a) the 32x32 pivot block by ONE warp (lane r owns row r; branch-free
+//   pivots with a fast rsqrt; rank-1 updates are applied at once only inside the current group of 8 columns, the columns to
+//   the right get their 8 updates in one batch, which keeps the 128-long dependent pivot chain short), (b) the rows below
+//   by one thread per row, (c) the in-tile SYRK by all warps.  The inverse is computed by the idle warps during (a).
+__global__ void __launch_bounds__(DIAG_THREADS, 1)
 potrf_diag_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ inv, double* __restrict__ invT, int has_sub,
                   double sub, int* info, int col_base) {
     extern __shared__ __align__(16) double dsm[];
     double* T = dsm;                       // [128][DIAG_DS], row-major: T[r*DS + c]
-    double* W = dsm + 128 * DIAG_DS;       // [96][33] scratch
+    double* W = dsm + 128 * DIAG_DS;       // [3][32][33] scratch (S_j blocks of the inverse)
     double* rdiag = W + 96 * 33;           // 1 / L[k][k]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int idx = tid; idx < 128 * 128; idx += 256) {
+    DIAG_MARK(0);
+    for (int idx = tid; idx < 128 * 128; idx += DIAG_THREADS) {
         const int r = idx & 127, c = idx >> 7;
         T[r * DIAG_DS + c] = (r >= c) ? A[r + (int64_t)c * lda] : 0.0;
     }
     __syncthreads();
+    DIAG_MARK(1);
 
     for (int s = 0; s < 4; ++s) {
         const int c0 = 32 * s;
-        // (a) pivot block: lane r owns row c0 + r
         if (warp == 0) {
+            // (a) pivot block: lane r owns row c0 + r
             double row[32];
             double* Tr = T + (c0 + lane) * DIAG_DS + c0;
 #pragma unroll
             for (int k = 0; k < 32; ++k) row[k] = Tr[k];
+            // A zero, negative or NaN pivot (nalgebra: is_zero / try_sqrt fails) takes the substitute or records the column;
+            // branch-free so the unrolled chain stays one basic block. (Pivots below 1e-300 count as zero: the MUFU seed
+            // flushes subnormals.)
+            const bool sub_ok = has_sub && sub > 0.0;
+            int badcol = 1 << 30;
+            auto checked = [&](double d, int k) -> double {
+                const bool ok = d > 1e-300;
+                if (!ok && !sub_ok) badcol = min(badcol, k);
+                return ok ? d : (sub_ok ? sub : nan(""));
+            };
+            double dk = checked(__shfl_sync(0xffffffffu, row[0], 0), 0);
+            double rs = rsqrt_pos(dk);
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
-                double dk = __shfl_sync(0xffffffffu, row[k], k);
-                if (!(dk > 0.0)) {  // zero, negative or NaN pivot (nalgebra: is_zero / try_sqrt fails)
-                    if (has_sub && sub > 0.0) dk = sub;
-                    else {
-                        if (lane == 0) atomicCAS(info, 0, col_base + c0 + k + 1);
-                        dk = nan("");
-                    }
-                }
-                // 1/sqrt first (one MUFU seed + Newton steps): the column scaling, which the next pivot waits for, needs
-                // only rs; sqrt(dk) = dk * rs gets one correction step off the critical path (<= 1 ulp)
-                const double rs = rsqrt(dk);
+                // sqrt(dk) = dk * rs with one correction step (<= 1 ulp); only rs is on the critical path
                 double sk = dk * rs;
                 sk = fma(0.5 * rs, fma(-sk, sk, dk), sk);
-                if (lane > k) row[k] *= rs;
-                else if (lane == k) { row[k] = sk; rdiag[c0 + k] = rs; }
+                row[k] = (lane == k) ? sk : row[k] * rs;  // lanes < k hold don't-care values above the diagonal
+                if (lane == k) rdiag[c0 + k] = rs;
                 if (lane >= k) Tr[k] = row[k];
                 __syncwarp();
+                const int kend = k | 7;  // last column of this group of 8
+                if (k < kend) {
 #pragma unroll
-                for (int c = k + 1; c < 32; ++c) {
-                    const double lck = T[(c0 + c) * DIAG_DS + c0 + k];
-                    row[c] = fma(-row[k], lck, row[c]);
+                    for (int c = k + 1; c <= kend; ++c) row[c] = fma(-row[k], T[(c0 + c) * DIAG_DS + c0 + k], row[c]);
+                } else if (k < 31) {
+#pragma unroll
+                    for (int c = k + 1; c < 32; ++c)
+#pragma unroll
+                        for (int kk = k - 7; kk <= k; ++kk)
+                            row[c] = fma(-row[kk], T[(c0 + c) * DIAG_DS + c0 + kk], row[c]);
+                }
+                if (k < 31) {
+                    dk = checked(__shfl_sync(0xffffffffu, row[k + 1], k + 1), k + 1);
+                    rs = rsqrt_pos(dk);
                 }
             }
+            if (badcol < 32 && lane == 0) atomicCAS(info, 0, col_base + c0 + badcol + 1);
+        } else if (s > 0) {
+            diag_inv_rowblock(T, W, rdiag, s - 1, warp - 1, DIAG_THREADS / 32 - 1, lane, 1);
         }
         __syncthreads();
+        DIAG_MARK(2 + 3 * s);
         const int tn = 128 - c0 - 32;  // rows (and columns) left below / right of the pivot block
         // (b) rows below the pivot block: x * L_pp^T = a, one thread per row, right-looking so updates are independent
         if (tid < tn) {
@@ -73,87 +254,33 @@ potrf_diag_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ inv,
             for (int k = 0; k < 32; ++k) Tr[k] = x[k];
         }
         __syncthreads();
+        DIAG_MARK(3 + 3 * s);
         // (c) trailing update inside the tile: A[r][c] -= sum_k X[r][k] X[c][k]
-        for (int e = tid; e < tn * tn; e += 256) {
-            const int rr = e / tn, cc = e - rr * tn;
-            if (cc <= rr) {
-                const double* xr = T + (c0 + 32 + rr) * DIAG_DS + c0;
-                const double* xc = T + (c0 + 32 + cc) * DIAG_DS + c0;
-                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll
-                for (int k = 0; k < 32; k += 4) {
-                    a0 = fma(xr[k], xc[k], a0);
-                    a1 = fma(xr[k + 1], xc[k + 1], a1);
-                    a2 = fma(xr[k + 2], xc[k + 2], a2);
-                    a3 = fma(xr[k + 3], xc[k + 3], a3);
-                }
-                T[(c0 + 32 + rr) * DIAG_DS + c0 + 32 + cc] -= (a0 + a1) + (a2 + a3);
-            }
-        }
+        if (s == 0) diag_syrk<96>(T, c0, warp, lane);
+        else if (s == 1) diag_syrk<64>(T, c0, warp, lane);
+        else if (s == 2) diag_syrk<32>(T, c0, warp, lane);
         __syncthreads();
+        DIAG_MARK(4 + 3 * s);
     }
 
     // the factor goes back to the matrix (lower part only)
-    for (int idx = tid; idx < 128 * 128; idx += 256) {
+    for (int idx = tid; idx < 128 * 128; idx += DIAG_THREADS) {
         const int r = idx & 127, c = idx >> 7;
         if (r >= c) A[r + (int64_t)c * lda] = T[r * DIAG_DS + c];
     }
+    DIAG_MARK(14);
+    diag_inv_rowblock(T, W, rdiag, 3, warp, DIAG_THREADS / 32, lane, 0);  // barrier 0 with all threads == __syncthreads
     __syncthreads();
-
-    // in-place inverse of the lower-triangular tile, 32-blocks from the last to the first (LAPACK dtrtri, lower)
-    for (int s = 3; s >= 0; --s) {
-        const int c0 = 32 * s;
-        const int tn = 128 - c0 - 32;
-        // (1) invert the 32x32 diagonal block: lane c owns column c of the inverse
-        if (warp == 0) {
-            double x[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                x[i] *= rdiag[c0 + i];
-#pragma unroll
-                for (int i2 = i + 1; i2 < 32; ++i2) x[i2] = fma(-x[i], T[(c0 + i2) * DIAG_DS + c0 + i], x[i2]);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (i >= lane) T[(c0 + i) * DIAG_DS + c0 + lane] = x[i];
-        }
-        __syncthreads();
-        if (tn > 0) {
-            // (2a) W = Ainv_trailing * C  (C = original block below the pivot block)
-            for (int e = tid; e < tn * 32; e += 256) {
-                const int rr = e >> 5, k = e & 31;
-                const double* ar = T + (c0 + 32 + rr) * DIAG_DS + c0 + 32;
-                double a0 = 0, a1 = 0;
-                int m = 0;
-                for (; m + 1 <= rr; m += 2) {
-                    a0 = fma(ar[m], T[(c0 + 32 + m) * DIAG_DS + c0 + k], a0);
-                    a1 = fma(ar[m + 1], T[(c0 + 32 + m + 1) * DIAG_DS + c0 + k], a1);
-                }
-                if (m <= rr) a0 = fma(ar[m], T[(c0 + 32 + m) * DIAG_DS + c0 + k], a0);
-                W[rr * 33 + k] = a0 + a1;
-            }
-            __syncthreads();
-            // (2b) C = -W * Dinv
-            for (int e = tid; e < tn * 32; e += 256) {
-                const int rr = e >> 5, k = e & 31;
-                double a0 = 0;
-                for (int m = k; m < 32; ++m) a0 = fma(W[rr * 33 + m], T[(c0 + m) * DIAG_DS + c0 + k], a0);
-                T[(c0 + 32 + rr) * DIAG_DS + c0 + k] = -a0;
-            }
-            __syncthreads();
-        }
-    }
-    for (int idx = tid; idx < 128 * 128; idx += 256) {
+    DIAG_MARK(18);
+    for (int idx = tid; idx < 128 * 128; idx += DIAG_THREADS) {
         const int r = idx & 127, c = idx >> 7;
-        inv[r + c * 128] = (r >= c) ? T[r * DIAG_DS + c] : 0.0;
+        inv[r + c * 128] = (r > c) ? T[c * DIAG_DS + r] : (r == c ? rdiag[r] : 0.0);
     }
-    for (int idx = tid; idx < 128 * 128; idx += 256) {  // transposed copy for the adjoint solves
+    for (int idx = tid; idx < 128 * 128; idx += DIAG_THREADS) {  // transposed copy for the adjoint solves
         const int c = idx & 127, r = idx >> 7;
-        invT[c + r * 128] = (r >= c) ? T[r * DIAG_DS + c] : 0.0;
+        invT[c + r * 128] = (r > c) ? T[c * DIAG_DS + r] : (r == c ? rdiag[r] : 0.0);
     }
+    DIAG_MARK(19);
 }
 
 cudaError_t potrf_prepare() {
@@ -183,7 +310,7 @@ void factor_panel(double* A, int64_t lda, int64_t np, int64_t J, int64_t Jend, d
         }
         {
             ProfScope ps(c, PROF_POTRF_DIAG, 128.0 * 128.0 * 128.0 / 3.0);
-            potrf_diag_kernel<<<1, 256, DIAG_SMEM_BYTES, c.st>>>(Ajj, lda, invdiag + j * TILE * TILE,
+            potrf_diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM_BYTES, c.st>>>(Ajj, lda, invdiag + j * TILE * TILE,
                                                                  invdiagT + j * TILE * TILE, has_sub, sub, info,
                                                                  (int)(j * TILE));
         }

@@ -19,6 +19,7 @@
 namespace fgp {
 
 constexpr int DIAG_DS = 129;                                   // smem row stride of the 128x128 diagonal tile
+constexpr int DIAG_THREADS = 512;
 constexpr int DIAG_SMEM_BYTES = (128 * DIAG_DS + 96 * 33 + 128) * 8;
 constexpr int PANEL_TILES = 4;                                 // outer panel = 512 columns
 
