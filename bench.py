@@ -235,7 +235,7 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    lib.fgp_set_profiling(h.ptr, 1)
+    lib.fgp_set_profiling(h.ptr, 0)
     if args.no_lookahead:
         lib.fgp_set_option(h.ptr, N.FGP_OPT_LOOKAHEAD, 0)
     fit_host()  # first touch: allocations, H2D
@@ -245,8 +245,8 @@ def run_ours(args, rank, local_rank, world):
     sampler.start()
 
     # ---- timed region 1: K fit steps, inputs resident in HBM (the factor is 8 n^2 bytes >> L2, no flush needed) ----
-    pms, pfl, pcnt = np.zeros(4), np.zeros(4), np.zeros(4, dtype=np.int64)
-    tms, tfl, tcnt = np.zeros(4), np.zeros(4), np.zeros(4, dtype=np.int64)
+    # per-launch profiling events are OFF here (they cost 2-10 % of a step in CPU launch overhead); the per-kernel
+    # breakdown behind `roofline` comes from K more steps with profiling on, right after
     launches = 0
     barrier()
     dev_ms = 0.0
@@ -255,16 +255,28 @@ def run_ours(args, rank, local_rank, world):
         refit()
         dev_ms += h.last_device_ms()
         launches += h.last_launch_count()
-        lib.fgp_profile_summary(h.ptr, N.dptr(pms), N.dptr(pfl), pcnt.ctypes.data_as(C.POINTER(C.c_int64)))
-        tms += pms
-        tfl += pfl
-        tcnt += pcnt
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     # collective steps start together (the first panel broadcast synchronises the ranks), so the slowest rank's device
     # time per step is the job's time per step; wall_ms (barrier to barrier, host clock) is reported beside it
     fit_ms = max_over_ranks(dev_ms / args.steps)
     wall_ms = max_over_ranks(wall_ms)
+
+    # ---- profiling pass: same K steps with CUDA events around every launch -------------------------------------------
+    pms, pfl, pcnt = np.zeros(4), np.zeros(4), np.zeros(4, dtype=np.int64)
+    tms, tfl, tcnt = np.zeros(4), np.zeros(4), np.zeros(4, dtype=np.int64)
+    prof_dev_ms = 0.0
+    if not args.no_profile:
+        lib.fgp_set_profiling(h.ptr, 1)
+        for _ in range(args.steps):
+            refit()
+            prof_dev_ms += h.last_device_ms()
+            lib.fgp_profile_summary(h.ptr, N.dptr(pms), N.dptr(pfl), pcnt.ctypes.data_as(C.POINTER(C.c_int64)))
+            tms += pms
+            tfl += pfl
+            tcnt += pcnt
+        lib.fgp_set_profiling(h.ptr, 0)
+        barrier()
 
     # ---- predict throughput, queries resident ------------------------------------------------------------------------
     h.check(lib.fgp_stage_queries(h.ptr, N.dptr(Xq), qr, qr))
@@ -323,10 +335,12 @@ def run_ours(args, rank, local_rank, world):
         "roofline": {"kernel": "gemm_nt_kernel", "bound": "tensor", "achieved": gemm_tflops, "peak": FP64_PEAK_TFLOPS,
                      "unit": "TFLOP/s", "frac": (gemm_tflops / FP64_PEAK_TFLOPS) if gemm_tflops else None,
                      "traffic": GEMM_TRAFFIC_BYTES_PER_LAUNCH.get(args.workload) if world == 1 else None,
-                     "launches": int(tcnt[0]), "share_of_step": float(tms[0] / max(dev_ms, 1e-9)),
+                     "launches": int(tcnt[0]), "share_of_step": float(tms[0] / max(prof_dev_ms, 1e-9)),
                      "note": "rank 0; achieved = algorithmic flops of all gemm_nt launches / sum of their CUDA-event "
-                             "durations (with look-ahead the panel-stream launches overlap the main-stream ones, so "
-                             "share_of_step can exceed 1)",
+                             "durations, from a separate pass of the same steps with per-launch events on (with look-ahead "
+                             "the panel-stream launches overlap the main-stream ones, so share_of_step can exceed 1 and "
+                             "the per-launch rate under-reports the kernel; isolated: profiles/gemm_bench_*.jsonl)",
+                     "profiled_ms_per_step": prof_dev_ms / args.steps,
                      "peak_source": "fp64 DMMA m8n8k4 register-resident burst measured on this pool "
                                     "(profiles/fp64_peak_r01.jsonl; MEASURED_PEAKS.json has no fp64 figure; nominal "
                                     "148 SM x 128 flop/clk x 1.965 GHz = 37.2; sustained DMMA loop 27.4)"},
@@ -359,6 +373,7 @@ def main():
     ap.add_argument("--workload", default="metric", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lookahead", action="store_true", help="A/B: single-stream Cholesky schedule")
+    ap.add_argument("--no-profile", action="store_true", help="A/B: no per-launch CUDA events (roofline fields become null)")
     ap.add_argument("--sharded", action="store_true", help="use the collective entry points even on one GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

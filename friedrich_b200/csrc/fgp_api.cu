@@ -54,17 +54,13 @@ PairArgs train_pair_args(const fgp_model* m) {
 
 // ---- alpha = K^-1 y : z = L^-1 y (kept for the likelihood, mod.rs:203), alpha = L^-T z --------------------------
 void solve_alpha(fgp_model* m) {
+    // z = L^-1 y, alpha = L^-T z: one wavefront launch each (csrc/vector_kernels.cuh); flags[0..nb) forward, [nb..2nb) adjoint
     const int nb = (int)(m->np / TILE);
-    cudaMemcpyAsync(m->work.p, m->y.p, m->np * sizeof(double), cudaMemcpyDeviceToDevice, m->st);
-    for (int j = 0; j < nb; ++j) {
-        trsv_fwd_kernel<<<nb - j, TRSV_THREADS, 0, m->st>>>(m->L.p, m->cap, m->inv.p, m->work.p, m->z.p, j);
-        m->launches += 1;
-    }
-    cudaMemcpyAsync(m->work.p, m->z.p, m->np * sizeof(double), cudaMemcpyDeviceToDevice, m->st);
-    for (int j = nb - 1; j >= 0; --j) {
-        trsv_adj_kernel<<<j + 1, TRSV_THREADS, 0, m->st>>>(m->L.p, m->cap, m->invT.p, m->work.p, m->alpha.p, j, nb);
-        m->launches += 1;
-    }
+    int* flags = reinterpret_cast<int*>(m->work.p);  // np doubles of scratch >= 2 nb ints
+    cudaMemsetAsync(flags, 0, 2 * (size_t)nb * sizeof(int), m->st);
+    trsv_fwd_wave_kernel<<<nb, TRSV_THREADS, 0, m->st>>>(m->L.p, m->cap, m->inv.p, m->y.p, m->z.p, flags);
+    trsv_adj_wave_kernel<<<nb, TRSV_THREADS, 0, m->st>>>(m->L.p, m->cap, m->invT.p, m->z.p, m->alpha.p, flags + nb, nb);
+    m->launches += 2;
 }
 
 int reserve_training(fgp_model* m, int64_t cap_rows, int64_t dp, bool keep) {

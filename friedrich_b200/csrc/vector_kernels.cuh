@@ -80,53 +80,74 @@ __device__ __forceinline__ double tile_matvec_512(const double* __restrict__ M, 
     return out;
 }
 
-// Forward (L x = b), right-looking over 128-blocks. Launch j = 0 .. nb-1 with grid = nb - j:
-//   (1) every block R = j + blockIdx.x applies the PREVIOUS solution (when j > 0): b_R -= L[R, j-1] x_{j-1};
-//   (2) block 0 then solves x_j = inv_j * b_j (b_j is final at that point).
+// ---- wavefront triangular solves: ONE launch per solve instead of one per block column -------------------------------
+// Block i of the grid owns the 128 unknowns of block row i. It consumes the solution blocks it depends on as their owners
+// publish them (a flag per block in global memory, release/acquire), so the 128-step dependency chain costs a flag
+// round trip per step instead of a kernel launch.  Blocks only ever wait for LOWER block indices, which the hardware
+// dispatches first, so the wait cannot deadlock however many blocks are resident.  The arithmetic (order of the block
+// updates j = 0, 1, ... and the mat-vec reductions) does not depend on the timing: results are deterministic.
+__device__ __forceinline__ void wave_wait(const int* flag) {
+    if (threadIdx.x == 0) {
+        int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        } while (v == 0);
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void wave_publish(int* flag) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
+}
+
+// Forward: L x = b.  x_i = inv_i (b_i - sum_{j<i} L[i,j] x_j)
 static __global__ void __launch_bounds__(TRSV_THREADS)
-trsv_fwd_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ inv, double* b, double* x, int j) {
+trsv_fwd_wave_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ inv, const double* __restrict__ b,
+                     double* x, int* flags) {
     __shared__ double xs[128];
     __shared__ double red[512];
     const int r = threadIdx.x & 127;
-    const int R = j + blockIdx.x;
-    const int64_t row0 = (int64_t)R * 128;
+    const int i = blockIdx.x;
+    const int64_t row0 = (int64_t)i * 128;
+    // the two tiles the LAST step needs (L[i, i-1] and inv_i) can be on their way to L2 long before x_{i-1} exists
+    if (threadIdx.x < 128) l2_prefetch(inv + (int64_t)i * 128 * 128 + (int64_t)threadIdx.x * 128, 1024);
+    else if (threadIdx.x < 256 && i > 0) l2_prefetch(L + row0 + ((int64_t)(i - 1) * 128 + (threadIdx.x - 128)) * ld, 1024);
     double v = 0.0;
     if (threadIdx.x < 128) v = b[row0 + r];
-    if (j > 0) {
-        if (threadIdx.x < 128) xs[r] = x[(int64_t)(j - 1) * 128 + r];
+    for (int j = 0; j < i; ++j) {
+        wave_wait(flags + j);
+        if (threadIdx.x < 128) xs[r] = __ldcg(x + (int64_t)j * 128 + r);
         __syncthreads();
-        const double s = tile_matvec_512(L + row0 + (int64_t)(j - 1) * 128 * ld, ld, xs, red);
-        if (threadIdx.x < 128) {
-            v -= s;
-            b[row0 + r] = v;
-        }
+        const double s = tile_matvec_512(L + row0 + (int64_t)j * 128 * ld, ld, xs, red);
+        v -= s;
     }
-    if (blockIdx.x == 0) {
-        if (threadIdx.x < 128) xs[r] = v;
-        __syncthreads();
-        const double s = tile_matvec_512(inv + (int64_t)R * 128 * 128, 128, xs, red);
-        if (threadIdx.x < 128) x[row0 + r] = s;
-    }
+    if (threadIdx.x < 128) xs[r] = v;
+    __syncthreads();
+    const double s = tile_matvec_512(inv + (int64_t)i * 128 * 128, 128, xs, red);
+    if (threadIdx.x < 128) x[row0 + r] = s;
+    wave_publish(flags + i);
 }
 
-// Adjoint (L^T x = b), from the last block. Launch j = nb-1 .. 0 with grid = j + 1:
-//   (1) when j < nb-1 every block C = blockIdx.x <= j applies the previous solution: b_C -= L[j+1, C]^T x_{j+1};
-//       warp w owns columns 8w .. 8w+7 of the tile, a lane reads rows lane, lane+32, lane+64, lane+96 of each (32
-//       independent loads), then eight shuffle reductions;
-//   (2) block C == j solves x_j = inv_j^T b_j (invT holds the transposed inverse, so it is the same mat-vec as above).
+// Adjoint: L^T x = b, from the last block.  Grid block g owns block column i = nb-1-g:
+// x_i = inv_i^T (b_i - sum_{j>i} L[j,i]^T x_j); warp w owns columns 8w .. 8w+7 of a tile, a lane reads rows lane, lane+32,
+// lane+64, lane+96 of each (32 independent loads), then eight shuffle reductions.
 static __global__ void __launch_bounds__(TRSV_THREADS)
-trsv_adj_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ invT, double* b, double* x, int j,
-                int nb) {
+trsv_adj_wave_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ invT, const double* __restrict__ b,
+                     double* x, int* flags, int nb) {
     __shared__ double xs[128];
     __shared__ double bs[128];
     __shared__ double red[512];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int Cb = blockIdx.x;
-    if (tid < 128) bs[tid] = b[(int64_t)Cb * 128 + tid];
-    if (j < nb - 1) {
-        if (tid < 128) xs[tid] = x[(int64_t)(j + 1) * 128 + tid];
+    const int i = nb - 1 - (int)blockIdx.x;
+    if (tid < 128) l2_prefetch(invT + (int64_t)i * 128 * 128 + (int64_t)tid * 128, 1024);
+    else if (tid < 256 && i + 1 < nb) l2_prefetch(L + (int64_t)(i + 1) * 128 + ((int64_t)i * 128 + (tid - 128)) * ld, 1024);
+    if (tid < 128) bs[tid] = b[(int64_t)i * 128 + tid];
+    for (int j = nb - 1; j > i; --j) {
+        wave_wait(flags + (nb - 1 - j));
+        if (tid < 128) xs[tid] = __ldcg(x + (int64_t)j * 128 + tid);
         __syncthreads();
-        const double* Lp = L + (int64_t)(j + 1) * 128 + ((int64_t)Cb * 128 + 8 * warp) * ld + lane;
+        const double* Lp = L + (int64_t)j * 128 + ((int64_t)i * 128 + 8 * warp) * ld + lane;
         double v[8][4];
 #pragma unroll
         for (int c = 0; c < 8; ++c)
@@ -139,14 +160,11 @@ trsv_adj_kernel(const double* __restrict__ L, int64_t ld, const double* __restri
             p = warp_sum(p);
             if (lane == 0) bs[8 * warp + c] -= p;
         }
-        __syncthreads();
-        if (tid < 128) b[(int64_t)Cb * 128 + tid] = bs[tid];
     }
     __syncthreads();
-    if (Cb == j) {
-        const double s = tile_matvec_512(invT + (int64_t)Cb * 128 * 128, 128, bs, red);
-        if (tid < 128) x[(int64_t)Cb * 128 + tid] = s;
-    }
+    const double s = tile_matvec_512(invT + (int64_t)i * 128 * 128, 128, bs, red);
+    if (tid < 128) x[(int64_t)i * 128 + tid] = s;
+    wave_publish(flags + (nb - 1 - i));
 }
 
 // ---- row reductions of the transposed buffer Bt (qp x np, column-major, ld) ---------------------------------------
