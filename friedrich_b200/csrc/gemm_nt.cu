@@ -34,6 +34,14 @@ gemm_nt_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ CUten
     const bool diag_tile = g.lower && (ti == tj);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (g.stagger_ns > 0 && (int)blockIdx.x >= g.stagger_lo && (int)blockIdx.x < g.stagger_hi) {
+        uint64_t t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        do {
+            __nanosleep(2000);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        } while (t1 - t0 < (uint64_t)g.stagger_ns);
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < GEMM_STAGES; ++s) {
             mbar_init(&full[s], 1);
@@ -264,6 +272,15 @@ int64_t gemm_nt_launch(const GemmArgs& g, const LaunchCtx& ctx) {
     // one work item per CTA (a persistent variant measured no faster and its never-retiring CTAs starve the look-ahead
     // stream's panel kernels: DESIGN.md "GEMM")
     const unsigned grid = (unsigned)items;
+    // de-synchronise the two resident CTAs of every SM (they would otherwise start, and therefore finish, together for the
+    // whole launch) by half the lifetime of a CTA pair: 2 x 64x128xK x 2 flop at 128 flop/clk/SM = K x 131 ns, plus overheads
+#ifndef FGP_GEMM_NO_STAGGER
+    if (items >= 8 * (int64_t)g_num_sms) {
+        p.stagger_lo = g_num_sms;
+        p.stagger_hi = 2 * g_num_sms;
+        p.stagger_ns = (g.K - (g.k_from_tile ? g.K / 2 : 0)) * 70;
+    }
+#endif
     // operand extents: rows beyond them arrive as zeros (only the padding rows of the last tile ever are). In lower mode the
     // rows of B are addressed by tile COLUMN positions of C, which reach M when the owned columns are strided (sharded).
     alignas(64) CUtensorMap tmA, tmB, tmC;

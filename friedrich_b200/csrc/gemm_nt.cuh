@@ -34,14 +34,20 @@
 
 namespace fgp {
 
-constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_KC = 16, GEMM_STAGES = 4;  // BM x BN: the tile the launch grid counts
+// tools/microbench/gemm_variants.cu sweeps the ring geometry through these macros; production uses the defaults
+#ifndef FGP_GEMM_KC
+#define FGP_GEMM_KC 16
+#define FGP_GEMM_STAGES 4
+#define FGP_GEMM_AHEAD 2
+#endif
+constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_KC = FGP_GEMM_KC, GEMM_STAGES = FGP_GEMM_STAGES;  // BM x BN: the tile the grid counts
 constexpr int GEMM_CTA_M = 64;                                          // rows of the tile one CTA computes
 constexpr int GEMM_LDA = GEMM_CTA_M + 4;                                // 68: smem column stride of the A stage (doubles)
 constexpr int GEMM_LDB = GEMM_BN + 4;                                   // 132: smem column stride of the B stage
 constexpr int GEMM_STAGE_DOUBLES = GEMM_KC * (GEMM_LDA + GEMM_LDB);     // A + B tile of one stage
 constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_DOUBLES * 8 + 2 * GEMM_STAGES * 8;
 constexpr int GEMM_WARPS = 4;
-constexpr int GEMM_AHEAD = 2;                                           // k-chunks in flight ahead of the one consumed
+constexpr int GEMM_AHEAD = FGP_GEMM_AHEAD;                                           // k-chunks in flight ahead of the one consumed
 constexpr int GEMM_THREADS = 32 * GEMM_WARPS;
 constexpr int GEMM_MAX_BANDS = 64, GEMM_BAND_ROWS = 16;
 
@@ -65,6 +71,10 @@ struct GemmArgs {
     int band_rows;                          // tile rows per band
     int n_bands;
     int band_prefix[GEMM_MAX_BANDS + 1];    // tiles in bands 0 .. r-1
+    // filled by gemm_nt_launch: blocks [stagger_lo, stagger_hi) — the second CTA each SM receives in the first wave — start
+    // stagger_ns late, so that the two CTAs of an SM stay half a tile out of phase for the rest of the launch and one's
+    // prologue / epilogue falls into the other's main loop (0 = off: launches of only a few waves)
+    int stagger_lo, stagger_hi, stagger_ns;
 };
 
 // Lower mode: the tiles of the launch, relative to C (whose origin is on the diagonal): local tile column jl sits at tile
