@@ -1,6 +1,8 @@
 // cov.cu — instantiations of the pair-tile engine that write covariance matrices (contract in covariance.cuh).
 #include "covariance.cuh"
 
+#include <cmath>
+
 namespace fgp {
 
 // ---- Gram / cross-covariance launch -----------------------------------------------------------------------------
@@ -16,13 +18,17 @@ void write_covariance(fgp_model* m, const KernelTraits& kt, const fgp_kernel_des
     const LaunchCtx lc = m->ctx();
     ProfScope ps(lc, PROF_PAIR, (double)pa.rows * pa.cols * (pa.symmetric ? 0.5 : 1.0) * 2.0 * pa.dp);
     if (kt.kind == KIND_SQEXP) {
-        CovWriteEpi<KIND_SQEXP> e{dk, out, ld, valid_rows, valid_cols, pa.symmetric, noise2};
+        const double ls = dk.param[0];
+        CovWriteEpi<KIND_SQEXP> e{dk, out, ld, valid_rows, valid_cols, pa.symmetric, noise2,
+                                  -1.0 / (2.0 * ls * ls), std::fabs(dk.param[1]), 0.0};
         launch_cov<KIND_SQEXP, PAIR_D2>(pa, e, m->st);
     } else if (kt.kind == KIND_MATERN2) {
-        CovWriteEpi<KIND_MATERN2> e{dk, out, ld, valid_rows, valid_cols, pa.symmetric, noise2};
+        const double l = std::fabs(dk.param[0]);
+        CovWriteEpi<KIND_MATERN2> e{dk, out, ld, valid_rows, valid_cols, pa.symmetric, noise2,
+                                    std::sqrt(5.0) / l, std::fabs(dk.param[1]), 5.0 / (3.0 * l * l)};
         launch_cov<KIND_MATERN2, PAIR_D2>(pa, e, m->st);
     } else {
-        CovWriteEpi<KIND_GENERIC> e{dk, out, ld, valid_rows, valid_cols, pa.symmetric, noise2};
+        CovWriteEpi<KIND_GENERIC> e{dk, out, ld, valid_rows, valid_cols, pa.symmetric, noise2, 0.0, 0.0, 0.0};
         if (mode == PAIR_D2) launch_cov<KIND_GENERIC, PAIR_D2>(pa, e, m->st);
         else if (mode == PAIR_DOT) launch_cov<KIND_GENERIC, PAIR_DOT>(pa, e, m->st);
         else launch_cov<KIND_GENERIC, PAIR_BOTH>(pa, e, m->st);

@@ -169,7 +169,11 @@ int predict_device(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& 
         m->have_mean = true;
     }
     if (want_var) {
-        m->launches += trsm_fwd_t(m->bt.p, qp, qp, m->L.p, m->cap, m->inv.p, 0, np / TILE, nullptr, m->ctx());
+        if (m->lookahead)
+            m->launches += trsm_fwd_t_lookahead(m->bt.p, qp, qp, m->L.p, m->cap, m->inv.p, np / TILE, m->ctx(), m->st2, m->evA,
+                                                m->evB);
+        else
+            m->launches += trsm_fwd_t(m->bt.p, qp, qp, m->L.p, m->cap, m->inv.p, 0, np / TILE, nullptr, m->ctx());
         rowreduce_partial_kernel<1><<<rgrid, 128, 0, m->st>>>(m->bt.p, qp, nullptr, m->partial.p, qp);
         rowreduce_final_kernel<<<(unsigned)(qp / 128), 128, 0, m->st>>>(m->partial.p, chunks, qp, m->q, 1, dk, m->qnr.p,
                                                                          m->var_d.p);
@@ -848,6 +852,8 @@ FGP_EXPORT int64_t fgp_dbg_lower_tiles(int M, int N, int grp, int stride, int* t
 
 // =================================================================================================================
 // test hook: the production GEMM on host matrices
+FGP_EXPORT double fgp_dbg_exp(double x) { return exp_nonpos(x); }
+
 FGP_EXPORT int fgp_dbg_gemm_occupancy(int device) {
     DeviceGuard dg(device);
     return gemm_nt_occupancy();

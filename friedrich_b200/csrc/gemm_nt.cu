@@ -8,8 +8,6 @@
 #define FGP_GEMM_EXP 0
 #endif
 
-#include <cuda.h>
-
 #include <algorithm>
 #include <cstdio>
 #include <vector>
@@ -167,6 +165,8 @@ int gemm_nt_occupancy() {
 static int g_num_sms = 0;
 static bool g_gemm_error = false;
 
+void gemm_nt_flag_error() { g_gemm_error = true; }
+
 bool gemm_nt_take_error() {
     const bool e = g_gemm_error;
     g_gemm_error = false;
@@ -189,9 +189,7 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// rows x cols column-major f64 matrix (leading dimension ld), box = box_rows x box_cols
-static bool make_operand_map(CUtensorMap* tm, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
-                             int box_cols = GEMM_KC) {
+bool make_tile_map(CUtensorMap* tm, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
@@ -285,8 +283,8 @@ int64_t gemm_nt_launch(const GemmArgs& g, const LaunchCtx& ctx) {
     // rows of B are addressed by tile COLUMN positions of C, which reach M when the owned columns are strided (sharded).
     alignas(64) CUtensorMap tmA, tmB, tmC;
     const int64_t ncols = g.lower ? g.M : g.N;
-    if (!make_operand_map(&tmA, g.A, g.M, g.K, g.lda, GEMM_LDA) || !make_operand_map(&tmB, g.B, ncols, g.K, g.ldb, GEMM_LDB) ||
-        !make_operand_map(&tmC, g.C, g.M, ncols, g.ldc, GEMM_CTA_M, GEMM_BN)) {
+    if (!make_tile_map(&tmA, g.A, g.M, g.K, g.lda, GEMM_LDA, GEMM_KC) || !make_tile_map(&tmB, g.B, ncols, g.K, g.ldb, GEMM_LDB, GEMM_KC) ||
+        !make_tile_map(&tmC, g.C, g.M, ncols, g.ldc, GEMM_CTA_M, GEMM_BN)) {
         if (!g_gemm_error) fprintf(stderr, "libfgp_sm100: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)\n", g.M, g.N, g.K);
         g_gemm_error = true;
         return 0;

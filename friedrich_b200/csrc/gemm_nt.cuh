@@ -30,6 +30,8 @@
 // All extents are multiples of the tile (matrices are padded), so there is no edge code.
 #pragma once
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace fgp {
@@ -118,6 +120,10 @@ __host__ __device__ inline void gemm_tile_decode(const GemmArgs& g, int b, int& 
 int64_t gemm_nt_tiles(const GemmArgs& g);  // number of 128x128 tiles one launch computes
 void gemm_nt_plan(GemmArgs& g);             // fills band_rows / n_bands / band_prefix (host)
 cudaError_t gemm_nt_prepare();
+// TMA descriptor of a rows x cols column-major f64 matrix (leading dimension ld) moved in box_rows x box_cols tiles
+// (cuTensorMapEncodeTiled through the runtime's driver entry point; false on failure)
+bool make_tile_map(CUtensorMap* tm, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols);
+void gemm_nt_flag_error();   // a kernel launch could not be set up (tensor-map encode failure): reported by end_timed
 bool gemm_nt_take_error();  // true once after a launch could not be set up (tensor-map encode failure)
 int gemm_nt_occupancy();  // resident CTAs per SM of the GEMM kernel on the current device (2 by design), -1 on error
 // algorithmic flops of one launch (what the roofline figure in bench.py is computed from)

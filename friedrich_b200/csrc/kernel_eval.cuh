@@ -5,6 +5,7 @@
 #pragma once
 
 #include <math.h>
+#include <string.h>
 
 #include "../../include/fgp_kernel_desc.h"
 #include "common.cuh"
@@ -32,23 +33,61 @@ __host__ __device__ inline int leaf_nparams(int tag) {
     }
 }
 
+// exp(x) for x <= 0 without branches (the library routine's special-case branch would keep the 32 independent kernel
+// evaluations of a pair-tile thread from being interleaved): round-to-nearest range reduction x = n ln2 + r, |r| <= 0.347,
+// degree-13 Taylor polynomial (truncation 4e-18), exponent insertion.  <= 1.5 ulp on [-708, 0] (tests/test_host_logic.py
+// through fgp_dbg_exp); below -708 (results under 3.3e-308, where exponent insertion would leave the normal range) it
+// returns 0, NaN stays NaN.
+__host__ __device__ __forceinline__ double exp_nonpos(double x) {
+    const double xc = (x < -708.0) ? -708.0 : x;
+    const double t = fma(xc, 1.4426950408889634074, 6755399441055744.0);  // 1.5 * 2^52: the low bits of t hold n
+    const double n = t - 6755399441055744.0;
+    double r = fma(n, -6.93147180369123816490e-01, xc);
+    r = fma(n, -1.90821492927058770002e-10, r);
+    double q = 1.6059043836821613e-10;            // 1/13!
+    q = fma(q, r, 2.08767569878681e-09);          // 1/12!
+    q = fma(q, r, 2.505210838544172e-08);         // 1/11!
+    q = fma(q, r, 2.755731922398589e-07);         // 1/10!
+    q = fma(q, r, 2.7557319223985893e-06);        // 1/9!
+    q = fma(q, r, 2.48015873015873e-05);          // 1/8!
+    q = fma(q, r, 1.984126984126984e-04);         // 1/7!
+    q = fma(q, r, 1.388888888888889e-03);         // 1/6!
+    q = fma(q, r, 8.333333333333333e-03);         // 1/5!
+    q = fma(q, r, 4.1666666666666664e-02);        // 1/4!
+    q = fma(q, r, 1.6666666666666666e-01);        // 1/3!
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    q = fma(q, r, 1.0);
+    const long long shift = (long long)(int)n << 52;
+#ifdef __CUDA_ARCH__
+    const double v = __longlong_as_double(__double_as_longlong(q) + shift);
+#else
+    long long bits;
+    memcpy(&bits, &q, 8);
+    bits += shift;
+    double v;
+    memcpy(&v, &bits, 8);
+#endif
+    return (x < -708.0) ? 0.0 : v;
+}
+
 __device__ __forceinline__ double dsignum(double v) { return (v != v) ? v : (signbit(v) ? -1.0 : 1.0); }
 
 __device__ __forceinline__ double leaf_value(int tag, const double* p, double dot, double d2) {
     switch (tag) {
         case FGP_K_LINEAR: return dot + p[0];                                    // kernel.rs:381
         case FGP_K_POLYNOMIAL: return pow(p[0] * dot + p[1], p[2]);              // kernel.rs:456
-        case FGP_K_SQUARED_EXP: return fabs(p[1]) * exp(-d2 / (2.0 * p[0] * p[0]));  // kernel.rs:556-560
-        case FGP_K_EXPONENTIAL: return fabs(p[1]) * exp(-sqrt(d2) / (2.0 * p[0] * p[0]));  // kernel.rs:661-665
+        case FGP_K_SQUARED_EXP: return fabs(p[1]) * exp_nonpos(-d2 / (2.0 * p[0] * p[0]));  // kernel.rs:556-560
+        case FGP_K_EXPONENTIAL: return fabs(p[1]) * exp_nonpos(-sqrt(d2) / (2.0 * p[0] * p[0]));  // kernel.rs:661-665
         case FGP_K_MATERN1: {                                                    // kernel.rs:766-771
             double l = fabs(p[0]), r = sqrt(d2);
             double x = sqrt(3.0) * r / l;
-            return fabs(p[1]) * (1.0 + x) * exp(-x);
+            return fabs(p[1]) * (1.0 + x) * exp_nonpos(-x);
         }
         case FGP_K_MATERN2: {                                                    // kernel.rs:873-878
             double l = fabs(p[0]), r = sqrt(d2);
             double x = sqrt(5.0) * r / l;
-            return fabs(p[1]) * (1.0 + x + (5.0 * r * r) / (3.0 * l * l)) * exp(-x);
+            return fabs(p[1]) * (1.0 + x + (5.0 * r * r) / (3.0 * l * l)) * exp_nonpos(-x);
         }
         case FGP_K_HYPERTAN: return tanh(p[0] * dot + p[1]);                     // kernel.rs:976
         case FGP_K_MULTIQUADRIC: return hypot(d2, p[0]);                         // kernel.rs:1049
@@ -68,14 +107,14 @@ __device__ __forceinline__ int leaf_grad(int tag, const double* p, double dot, d
             return 3;
         }
         case FGP_K_SQUARED_EXP: {                                                // kernel.rs:569-575
-            double e = exp(-d2 / (2.0 * p[0] * p[0]));
+            double e = exp_nonpos(-d2 / (2.0 * p[0] * p[0]));
             g[0] = (d2 * fabs(p[1]) * e) / (p[0] * p[0] * p[0]);
             g[1] = dsignum(p[1]) * e;
             return 2;
         }
         case FGP_K_EXPONENTIAL: {                                                // kernel.rs:674-680
             double r = sqrt(d2);
-            double e = exp(-r / (2.0 * p[0] * p[0]));
+            double e = exp_nonpos(-r / (2.0 * p[0] * p[0]));
             g[0] = (r * fabs(p[1]) * e) / (p[0] * p[0] * p[0]);
             g[1] = dsignum(p[1]) * e;
             return 2;

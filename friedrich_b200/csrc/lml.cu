@@ -37,7 +37,10 @@ struct LmlEpi {
             }
         }
     }
-    __device__ __forceinline__ void finish() {
+    __device__ __forceinline__ void skipped(int64_t, int64_t) {}
+    template <class E>
+    __device__ __forceinline__ void bind(const E*) {}
+    __device__ __forceinline__ void finish(int64_t, int64_t, bool) {
         block_sum_store<NV>(acc, partial + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * NV);
     }
 };
@@ -50,7 +53,10 @@ struct DistEpi {
     __device__ __forceinline__ void operator()(int64_t r, int64_t c, double, double d2) {
         if (r < n && c < r) acc[0] += sqrt(d2);
     }
-    __device__ __forceinline__ void finish() { block_sum_store<1>(acc, partial + (size_t)(blockIdx.y * gridDim.x + blockIdx.x)); }
+    __device__ __forceinline__ void skipped(int64_t, int64_t) {}
+    template <class E>
+    __device__ __forceinline__ void bind(const E*) {}
+    __device__ __forceinline__ void finish(int64_t, int64_t, bool) { block_sum_store<1>(acc, partial + (size_t)(blockIdx.y * gridDim.x + blockIdx.x)); }
 };
 
 // out[v] = sum_b partial[b*nv + v], b ascending; one thread per value, 4 interleaved partial sums

@@ -140,7 +140,7 @@ inline int end_timed(fgp_model* m) {
     CU(m, cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
     if (m->profiling) m->prof.collect();
     CU(m, cudaGetLastError());
-    if (gemm_nt_take_error()) return fgp::fail(m, FGP_ERR_CUDA, "GEMM launch setup failed (cuTensorMapEncodeTiled)");
+    if (gemm_nt_take_error()) return fgp::fail(m, FGP_ERR_CUDA, "kernel launch setup failed (cuTensorMapEncodeTiled)");
     return FGP_OK;
 }
 

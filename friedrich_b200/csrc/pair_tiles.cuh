@@ -39,9 +39,13 @@ constexpr int PAIR_TM = 128;  // tile rows
 constexpr int PAIR_TN = 64;   // tile columns
 
 // Epilogue concept:  __device__ void operator()(int64_t r, int64_t c, double dot, double d2);   (called for r>=c only
-// when symmetric)    __device__ void finish();   (once per thread at the end; may use __syncthreads)
+// when symmetric)    __device__ void skipped(int64_t r, int64_t c);   (the r<c elements of an active symmetric tile)
+// __device__ void finish(int64_t row0, int64_t col0, bool active);   (once per thread at the end; may use __syncthreads)
+// __device__ void bind(const Epi* param);   (the functor as passed to the kernel, in parameter space)
 template <int MODE, class Epi>
-__global__ void __launch_bounds__(256) pair_tile_kernel(PairArgs a, Epi epi) {
+__global__ void __launch_bounds__(256) pair_tile_kernel(PairArgs a, const __grid_constant__ Epi epi_in) {
+    Epi epi = epi_in;   // accumulating epilogues keep per-thread state
+    epi.bind(&epi_in);  // ... while a TMA descriptor must be addressed in the kernel-parameter space
     const int64_t row0 = (int64_t)(blockIdx.x + a.row_tile0) * PAIR_TM;
     const int64_t col0 = (int64_t)(blockIdx.y + a.col_tile0) * PAIR_TN;
     const bool active = !(a.symmetric && row0 + PAIR_TM - 1 < col0);
@@ -91,46 +95,69 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(PairArgs a, Epi epi) {
             }
         }
 
-        // epilogue: fuse the norm broadcast and hand (dot, d2) to the functor
+        // epilogue: fuse the norm broadcast and hand (dot, d2) to the functor.  Three passes so that the 32 kernel
+        // evaluations of a thread form ONE branch-free block the scheduler can interleave: (1) d2 for every pair, (2) the
+        // rare near-coincidence repair, (3) the functor.
         double nrow[4];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) nrow[mi] = (MODE == PAIR_DOT) ? 0.0 : __ldg(a.na + wr0 + 8 * mi + g);
+        double d2v[4][4][2];
+        unsigned fix = 0u;  // bit (ni*2+e)*4+mi: the expansion lost > 12 bits for this pair
+        if (MODE != PAIR_DOT) {
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int64_t c = wc0 + 8 * ni + 2 * t + e;
+                    const double ncol = __ldg(a.nb + c);
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) {
+                        const int64_t r = wr0 + 8 * mi + g;
+                        const double nsum = nrow[mi] + ncol;
+                        double d2 = fmax(nsum - 2.0 * acc[mi][ni][e], 0.0);
+                        const bool diag = a.symmetric && r == c;
+                        const bool skip = a.symmetric && r < c;
+                        if (!diag && !skip && d2 < nsum * 0x1p-12) fix |= 1u << ((ni * 2 + e) * 4 + mi);
+                        d2v[mi][ni][e] = diag ? 0.0 : d2;
+                    }
+                }
+            if (fix) {  // cancellation ate > 12 bits: direct differences, as the reference's (x1 - x2).norm_squared()
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+#pragma unroll
+                        for (int mi = 0; mi < 4; ++mi)
+                            if (fix & (1u << ((ni * 2 + e) * 4 + mi))) {
+                                const double* xr = a.xa_c + (wr0 + 8 * mi + g) * dp;
+                                const double* xc = a.xb_c + (wc0 + 8 * ni + 2 * t + e) * dp;
+                                double s = 0.0;
+                                for (int k = 0; k < dp; ++k) {
+                                    const double df = __ldg(xr + k) - __ldg(xc + k);
+                                    s = fma(df, df, s);
+                                }
+                                d2v[mi][ni][e] = s;
+                            }
+            }
+        }
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int64_t c = wc0 + 8 * ni + 2 * t + e;
-                const double ncol = (MODE == PAIR_DOT) ? 0.0 : __ldg(a.nb + c);
 #pragma unroll
                 for (int mi = 0; mi < 4; ++mi) {
                     const int64_t r = wr0 + 8 * mi + g;
-                    if (a.symmetric && r < c) continue;
-                    double dot = 0.0, d2 = 0.0;
-                    if (MODE == PAIR_DOT) {
-                        dot = acc[mi][ni][e];
-                    } else {
-                        if (MODE == PAIR_BOTH) dot = accr[mi][ni][e];
-                        const double nsum = nrow[mi] + ncol;
-                        d2 = fmax(nsum - 2.0 * acc[mi][ni][e], 0.0);
-                        if (a.symmetric && r == c) {
-                            d2 = 0.0;
-                        } else if (d2 < nsum * 0x1p-12) {  // cancellation ate > 12 bits: direct differences
-                            const double* xr = a.xa_c + r * dp;
-                            const double* xc = a.xb_c + c * dp;
-                            double s = 0.0;
-                            for (int k = 0; k < dp; ++k) {
-                                const double df = __ldg(xr + k) - __ldg(xc + k);
-                                s = fma(df, df, s);
-                            }
-                            d2 = s;
-                        }
+                    if (a.symmetric && r < c) {
+                        epi.skipped(r, c);
+                        continue;
                     }
-                    epi(r, c, dot, d2);
+                    const double dot = (MODE == PAIR_DOT) ? acc[mi][ni][e] : ((MODE == PAIR_BOTH) ? accr[mi][ni][e] : 0.0);
+                    epi(r, c, dot, (MODE == PAIR_DOT) ? 0.0 : d2v[mi][ni][e]);
                 }
             }
-        }
     }
-    epi.finish();
+    epi.finish(row0, col0, active);
 }
 
 inline dim3 pair_grid(const PairArgs& pa) {
@@ -161,6 +188,9 @@ __device__ __forceinline__ void block_sum_store(double (&v)[NV], double* out) {
 // ---------------------------------------------------------------------------------------------------------------
 // Epilogue: write the covariance matrix.  symmetric => Gram lower triangle with noise^2 on the diagonal and an
 // identity block on the padding (so the padded matrix stays positive definite and its factor is [[L,0],[0,I]]).
+// Each lane group writes 64-byte column runs directly. (A shared-memory staged tile + one TMA tensor store measured 9 %
+// slower: the kernel is bound by the ~100 instructions per pair — fp64 exp, the norm expansion and its guards — not by
+// its stores; profiles/ncu_gram_*.jsonl.)
 template <int KIND>
 struct CovWriteEpi {
     DevKernel k;
@@ -169,17 +199,24 @@ struct CovWriteEpi {
     int64_t valid_rows, valid_cols;
     int symmetric;
     double noise2;
+    // host-precomputed constants of the two specialised kernels (one rounding away from the expressions as coded in
+    // kernel.rs:556-560 / :873-878, which divide per pair): SquaredExp c0 = -1/(2 ls^2), c1 = |ampl|;
+    // Matern2 c0 = sqrt(5)/|ls|, c1 = |ampl|, c2 = 5/(3 ls^2)
+    double c0, c1, c2;
+    __device__ __forceinline__ void bind(const CovWriteEpi*) {}
     __device__ __forceinline__ void operator()(int64_t r, int64_t c, double dot, double d2) const {
         double v;
-        if (r >= valid_rows || c >= valid_cols) {
-            v = (symmetric && r == c) ? 1.0 : 0.0;
-        } else {
-            v = kernel_value<KIND>(k, dot, d2);
-            if (symmetric && r == c) v += noise2;  // algebra/mod.rs:78
-        }
+        if (KIND == KIND_SQEXP) v = c1 * exp_nonpos(d2 * c0);
+        else if (KIND == KIND_MATERN2) {
+            const double x = c0 * sqrt(d2);
+            v = c1 * (1.0 + x + c2 * d2) * exp_nonpos(-x);
+        } else v = kernel_value<KIND>(k, dot, d2);
+        if (symmetric && r == c) v += noise2;  // algebra/mod.rs:78
+        if (r >= valid_rows || c >= valid_cols) v = (symmetric && r == c) ? 1.0 : 0.0;
         out[r + c * ld] = v;
     }
-    __device__ __forceinline__ void finish() const {}
+    __device__ __forceinline__ void skipped(int64_t, int64_t) const {}
+    __device__ __forceinline__ void finish(int64_t, int64_t, bool) const {}
 };
 
 }  // namespace fgp

@@ -55,4 +55,60 @@ inline int64_t trsm_fwd_t(double* Xt, int64_t ldx, int64_t M, const double* L, i
     return launches;
 }
 
+// The same solve in 512-column panels with a one-panel look-ahead on a second stream (the schedule of potrf_lower):
+//   panel stream   inside the panel: Xt[:, i] *= inv_i^T, Xt[:, i+1 .. panel end) -= Xt[:, i] L[.., i]^T   (K = 128, short)
+//                  then the NEXT panel's columns -= Xt[:, panel] L[next, panel]^T                           (K = 512)
+//   main stream    all later columns            -= Xt[:, panel] L[later, panel]^T                           (K = 512)
+// so the 128-long chain of small in-panel products hides behind the large K = 512 updates, which also run the GEMM kernel at
+// its efficient depth.  Every product sees the operands of the sequential algorithm; only the grouping of the k-sums
+// differs (4 blocks of 128 accumulated in one launch).  Returns the number of launches; ends joined on st.st.
+inline int64_t trsm_fwd_t_lookahead(double* Xt, int64_t ldx, int64_t M, const double* L, int64_t ldl, const double* inv,
+                                    int64_t nb, const LaunchCtx& st, cudaStream_t panel_stream, cudaEvent_t ev_panel,
+                                    cudaEvent_t ev_trail) {
+    constexpr int64_t PT = 4;
+    int64_t launches = 0;
+    LaunchCtx pc = st;
+    pc.st = panel_stream;
+    auto gemm = [&](double* C, const double* A, const double* B, int64_t ldb, int64_t N, int64_t K, bool solve,
+                    const LaunchCtx& c) {
+        GemmArgs g{};
+        g.C = C; g.ldc = ldx;
+        g.A = A; g.lda = ldx;
+        g.B = B; g.ldb = ldb;
+        g.M = (int)M; g.N = (int)N; g.K = (int)K;
+        g.alpha = solve ? 1.0 : -1.0; g.beta_one = solve ? 0 : 1; g.lower = 0; g.k_from_tile = 0;
+        launches += gemm_nt_launch(g, c) > 0;
+    };
+    auto inner = [&](int64_t P, int64_t Pend) {
+        for (int64_t i = P; i < Pend; ++i) {
+            double* Xi = Xt + i * TILE * ldx;
+            gemm(Xi, Xi, inv + i * TILE * TILE, TILE, TILE, TILE, true, pc);
+            if (i + 1 < Pend) gemm(Xi + TILE * ldx, Xi, L + (i + 1) * TILE + i * TILE * ldl, ldl, (Pend - i - 1) * TILE, TILE, false, pc);
+        }
+    };
+    cudaEventRecord(ev_trail, st.st);  // the panel stream starts after whatever filled Xt on the main stream
+    cudaStreamWaitEvent(panel_stream, ev_trail, 0);
+    bool first = true;
+    for (int64_t P = 0; P < nb; P += PT) {
+        const int64_t Pend = std::min(P + PT, nb);
+        inner(P, Pend);
+        cudaEventRecord(ev_panel, panel_stream);
+        if (Pend < nb) {
+            const int64_t Pend2 = std::min(Pend + PT, nb);
+            const double* Xp = Xt + P * TILE * ldx;
+            cudaStreamWaitEvent(st.st, ev_panel, 0);                          // main: panel [P, Pend) is solved
+            if (!first) cudaStreamWaitEvent(panel_stream, ev_trail, 0);       // panel: earlier updates reached columns >= Pend
+            gemm(Xt + Pend * TILE * ldx, Xp, L + Pend * TILE + P * TILE * ldl, ldl, (Pend2 - Pend) * TILE, (Pend - P) * TILE,
+                 false, pc);
+            if (Pend2 < nb)
+                gemm(Xt + Pend2 * TILE * ldx, Xp, L + Pend2 * TILE + P * TILE * ldl, ldl, (nb - Pend2) * TILE,
+                     (Pend - P) * TILE, false, st);
+            cudaEventRecord(ev_trail, st.st);
+            first = false;
+        }
+    }
+    cudaStreamWaitEvent(st.st, ev_panel, 0);  // join
+    return launches;
+}
+
 }  // namespace fgp

@@ -167,6 +167,9 @@ int fgp_dbg_gemm_nt(int device, double* C, int64_t ldc, const double* A, int64_t
  * *flops_out = algorithmic flops per launch. Used by tools/gemm_bench.py for the kernel's isolated roofline figure. */
 int fgp_dbg_gemm_bench(int device, int M, int N, int K, int lower, int beta_one, int reps, double* ms_out, double* flops_out);
 
+/* test hook, host only: the branch-free exp(x), x <= 0, that the device kernels evaluate (csrc/kernel_eval.cuh exp_nonpos) */
+double fgp_dbg_exp(double x);
+
 /* test hook: resident CTAs per SM of the GEMM kernel on `device` (the design point is 2: one CTA's C read-modify-write
  * overlaps the other's DMMA main loop); -1 on error */
 int fgp_dbg_gemm_occupancy(int device);

@@ -71,3 +71,21 @@ def test_kernel_desc_layout_matches_header():
     from oracle import oracle as O
     assert C.sizeof(N.KernelDesc) == 4 + 4 * 15 + 8 * 24 == C.sizeof(O.KernelDesc)
     assert N.KernelDesc.param.offset == 64
+
+
+def test_branch_free_exp_is_accurate_to_two_ulp():
+    """csrc/kernel_eval.cuh exp_nonpos (host twin through fgp_dbg_exp): the exp every device kernel evaluation uses."""
+    import math
+    import numpy as np
+    from friedrich_b200 import _native as N
+    lib = N.lib()
+    rng = np.random.default_rng(7)
+    xs = np.concatenate([-rng.random(20000) * 50.0, -rng.random(5000) * 708.0, -np.logspace(-300, 0, 2000),
+                         [0.0, -0.0, -0.5 * math.log(2.0), -math.log(2.0), -708.0, -1e-320]])
+    worst = 0.0
+    for x in xs:
+        got, ref = lib.fgp_dbg_exp(float(x)), math.exp(float(x))
+        worst = max(worst, abs(got - ref) / np.spacing(ref))
+    assert worst <= 2.0, worst
+    assert lib.fgp_dbg_exp(-709.0) == 0.0 and lib.fgp_dbg_exp(-float("inf")) == 0.0
+    assert math.isnan(lib.fgp_dbg_exp(float("nan")))

@@ -52,7 +52,7 @@ def main():
                 v = float(r[H[k]].replace(",", ""))
                 u = units[H[k]]
                 d[nm] = v * SCALE.get(u, 1.0) if nm in ("duration", "dram_read", "dram_write") else v
-        if "duration" in d and "dram_read" in d:
+        if d.get("duration") and "dram_read" in d:
             d["dram_bytes"] = d["dram_read"] + d.get("dram_write", 0.0)
             d["dram_GBps"] = d["dram_bytes"] / d["duration"] * 1e-9
         lines.append(d)
