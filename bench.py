@@ -346,6 +346,8 @@ def run_ours(args, rank, local_rank, world):
                                     "148 SM x 128 flop/clk x 1.965 GHz = 37.2; sustained DMMA loop 27.4)"},
         "kernel_ms_per_step": {"gemm_nt": tms[0] / args.steps, "potrf_diag": tms[1] / args.steps,
                                "gram": tms[2] / args.steps},
+        "bcast_as_owner": ({"ms_per_step": tms[3] / args.steps, "launches": int(tcnt[3]),
+                            "GBps": (tfl[3] / max(tms[3], 1e-9)) * 1e-6} if use_sharded and tcnt[3] else None),
         "clocks": clocks,
     }
     if use_sharded:

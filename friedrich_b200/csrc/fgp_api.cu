@@ -86,7 +86,7 @@ int factor_resident(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits&
     CU(m, cudaMemsetAsync(m->info_d, 0, sizeof(int), m->st));
     write_covariance(m, kt, kd, train_pair_args(m), m->L.p, m->cap, m->n, m->n, noise * noise);
     PotrfCounters cnt;
-    const PotrfLookahead la{m->st2, m->evA, m->evB};
+    const PotrfLookahead la{m->st2, m->evA, m->evB, m->st3, m->evC};
     potrf_lower(m->L.p, m->cap, m->np, 0, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->ctx(), m->lookahead ? &la : nullptr,
                 &cnt);
     m->launches += cnt.launches;
@@ -223,6 +223,11 @@ void comm_release(fgp_model* m) {
     if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
     c->pbuf[0].release();
     c->pbuf[1].release();
+    if (c->st_comm) {
+        cudaStreamSynchronize(c->st_comm);
+        cudaStreamDestroy(c->st_comm);
+    }
+    if (c->ev_col) cudaEventDestroy(c->ev_col);
     if (c->ev_bcast) cudaEventDestroy(c->ev_bcast);
     for (cudaEvent_t e : c->ev_trail)
         if (e) cudaEventDestroy(e);
@@ -248,6 +253,8 @@ FGP_EXPORT int fgp_create(int device, fgp_model** out) {
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // st2 = panel stream of the look-ahead Cholesky: highest priority
     bool ok = cudaStreamCreateWithPriority(&m->st, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
               cudaStreamCreateWithPriority(&m->st2, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&m->st3, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+              cudaEventCreateWithFlags(&m->evC, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreate(&m->ev0) == cudaSuccess && cudaEventCreate(&m->ev1) == cudaSuccess &&
               cudaEventCreateWithFlags(&m->evA, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&m->evB, cudaEventDisableTiming) == cudaSuccess &&
@@ -268,6 +275,7 @@ FGP_EXPORT int fgp_destroy(fgp_model* m) {
         DeviceGuard dg(m->device);
         if (m->st) cudaStreamSynchronize(m->st);
         if (m->st2) cudaStreamSynchronize(m->st2);
+        if (m->st3) cudaStreamSynchronize(m->st3);
         comm_release(m);
         for (DevBuf* b : {&m->xr, &m->xc, &m->nc, &m->nr, &m->cmean, &m->y, &m->z, &m->alpha, &m->work, &m->L, &m->inv,
                           &m->invT, &m->staging, &m->qr, &m->qc, &m->qnc, &m->qnr, &m->bt, &m->partial, &m->mean_d,
@@ -280,9 +288,11 @@ FGP_EXPORT int fgp_destroy(fgp_model* m) {
         if (m->ev1) cudaEventDestroy(m->ev1);
         if (m->evA) cudaEventDestroy(m->evA);
         if (m->evB) cudaEventDestroy(m->evB);
+        if (m->evC) cudaEventDestroy(m->evC);
         m->prof.destroy();
         if (m->st) cudaStreamDestroy(m->st);
         if (m->st2) cudaStreamDestroy(m->st2);
+        if (m->st3) cudaStreamDestroy(m->st3);
     }
     delete m;
     return FGP_OK;
@@ -634,7 +644,7 @@ FGP_EXPORT int fgp_add_samples(fgp_model* m, const double* Xnew, int64_t ldx, in
     m->launches += trsm_fwd_t(Arows, m->cap, np_new - jb * TILE, m->L.p, m->cap, m->inv.p, 0, jb, Arows + jb * TILE * m->cap,
                               m->ctx());
     PotrfCounters cnt;
-    const PotrfLookahead la{m->st2, m->evA, m->evB};
+    const PotrfLookahead la{m->st2, m->evA, m->evB, m->st3, m->evC};
     potrf_lower(m->L.p, m->cap, np_new, jb, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->ctx(), m->lookahead ? &la : nullptr,
                 &cnt);
     m->launches += cnt.launches;
@@ -715,7 +725,11 @@ FGP_EXPORT int fgp_comm_init_rank(fgp_model* m, const void* id, size_t bytes, in
     c->nranks = nranks;
     c->rank = rank;
     m->comm = c;
-    if (cudaEventCreateWithFlags(&c->ev_bcast, cudaEventDisableTiming) != cudaSuccess ||
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&c->st_comm, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_col, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_bcast, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_trail[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_trail[1], cudaEventDisableTiming) != cudaSuccess) {
         comm_release(m);

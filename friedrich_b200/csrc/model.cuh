@@ -49,7 +49,9 @@ struct fgp_model {
     int device = 0;
     cudaStream_t st = nullptr;
     cudaStream_t st2 = nullptr;  // look-ahead / copy stream
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
+    cudaStream_t st3 = nullptr;  // side stream of the look-ahead: the next panel's block columns 1.. are updated here while
+                                 // block column 0 is already being factored on st2
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr, evC = nullptr;
     std::mutex mu;
     std::string err;
 

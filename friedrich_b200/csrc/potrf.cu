@@ -295,10 +295,12 @@ cudaError_t potrf_prepare() {
 
 // block columns [J, Jend) of one panel, left-looking inside the panel; every launch goes to c.st
 void factor_panel(double* A, int64_t lda, int64_t np, int64_t J, int64_t Jend, double* invdiag, double* invdiagT,
-                         int has_sub, double sub, int* info, const LaunchCtx& c, PotrfCounters* cnt) {
+                         int has_sub, double sub, int* info, const LaunchCtx& c, PotrfCounters* cnt, cudaEvent_t after_first,
+                         const std::function<void(int64_t)>* column_done) {
     const int64_t nb = np / TILE;
     for (int64_t j = J; j < Jend; ++j) {
         double* Ajj = A + j * TILE + j * TILE * lda;
+        if (j == J + 1 && after_first) cudaStreamWaitEvent(c.st, after_first, 0);
         if (j > J) {
             GemmArgs g{};
             g.C = Ajj; g.ldc = lda;
@@ -324,6 +326,7 @@ void factor_panel(double* A, int64_t lda, int64_t np, int64_t J, int64_t Jend, d
             g.alpha = 1.0; g.beta_one = 0; g.lower = 0; g.k_from_tile = 0;
             cnt->launches += gemm_nt_launch(g, c) > 0;
         }
+        if (column_done) (*column_done)(j);
     }
 }
 
@@ -338,6 +341,13 @@ void trailing_update(double* A, int64_t lda, int64_t np, int64_t J, int64_t Jend
     g.M = (int)(np - c0 * TILE); g.N = (int)((c1 - c0) * TILE); g.K = (int)((Jend - J) * TILE);
     g.alpha = -1.0; g.beta_one = 1; g.lower = 1; g.k_from_tile = 0;
     cnt->launches += gemm_nt_launch(g, c) > 0;
+}
+
+// block columns [c0, c1) of the trailing matrix, rows >= c0 (the trapezoid whose first diagonal tile is (c0, c0)) -= P P^T,
+// P = block columns [J, Jend): same tiles and arithmetic as the corresponding part of trailing_update(.., c_first <= c0, ..)
+void trailing_update_cols(double* A, int64_t lda, int64_t np, int64_t J, int64_t Jend, int64_t c0, int64_t c1,
+                          const LaunchCtx& c, PotrfCounters* cnt) {
+    trailing_update(A, lda, np, J, Jend, c0, c1, c, cnt);
 }
 
 void potrf_lower(double* A, int64_t lda, int64_t np, int64_t jb_begin, double* invdiag, double* invdiagT, int has_sub,
@@ -369,8 +379,21 @@ void potrf_lower(double* A, int64_t lda, int64_t np, int64_t jb_begin, double* i
         const int64_t Jend2 = (Jend + PANEL_TILES < nb) ? Jend + PANEL_TILES : nb;
         cudaStreamWaitEvent(st.st, la->ev_panel, 0);                   // M: panel [J, Jend) is final
         if (!first) cudaStreamWaitEvent(la->panel, la->ev_trail, 0);   // P: previous trailing update reached columns >= Jend
-        trailing_update(A, lda, np, J, Jend, Jend, Jend2, pc, cnt);    // look-ahead columns
-        factor_panel(A, lda, np, Jend, Jend2, invdiag, invdiagT, has_sub, sub, info, pc, cnt);
+        if (la->side && Jend2 - Jend > 1) {
+            // look-ahead columns: block column 0 of the next panel on P (its factorisation follows at once), the others on
+            // the side stream, joined before P touches block column 1
+            LaunchCtx sc = st;
+            sc.st = la->side;
+            cudaEventRecord(la->ev_side, la->panel);                  // side: whatever P waited for (previous trailing update)
+            cudaStreamWaitEvent(la->side, la->ev_side, 0);
+            trailing_update(A, lda, np, J, Jend, Jend, Jend + 1, pc, cnt);
+            trailing_update_cols(A, lda, np, J, Jend, Jend + 1, Jend2, sc, cnt);
+            cudaEventRecord(la->ev_side, la->side);
+            factor_panel(A, lda, np, Jend, Jend2, invdiag, invdiagT, has_sub, sub, info, pc, cnt, la->ev_side);
+        } else {
+            trailing_update(A, lda, np, J, Jend, Jend, Jend2, pc, cnt);    // look-ahead columns
+            factor_panel(A, lda, np, Jend, Jend2, invdiag, invdiagT, has_sub, sub, info, pc, cnt);
+        }
         cudaEventRecord(la->ev_panel, la->panel);
         trailing_update(A, lda, np, J, Jend, Jend2, nb, st, cnt);      // the rest
         cudaEventRecord(la->ev_trail, st.st);

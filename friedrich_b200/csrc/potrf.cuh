@@ -13,6 +13,8 @@
 // recorded in `info` (first failure wins) and the host maps it to the reference's panic.
 #pragma once
 
+#include <functional>
+
 #include "common.cuh"
 #include "gemm_nt.cuh"
 
@@ -33,17 +35,27 @@ cudaError_t potrf_prepare();
 // jb_begin must already hold final factor values in ALL rows (used by add_samples: the caller has applied them to
 // the trailing block). invdiag / invdiagT: [np/128][128*128] (inverse blocks and their transposes). info: device int, 0 on entry.
 // block columns [J, Jend) of one panel (left-looking inside the panel: update, diagonal tile, panel solve); launches on c.st
+// `after_first` (optional): an event the stream waits for after block column J has been factored and solved, before block
+// column J+1 is touched (the look-ahead's side-stream update of block columns J+1.. by the previous panel).
+// `column_done` (optional): called on the host right after the launches that finalise block column j (diagonal tile + panel
+// solve) have been enqueued on c.st — the sharded fit ships the column to the other GPUs from there.
 void factor_panel(double* A, int64_t lda, int64_t np, int64_t J, int64_t Jend, double* invdiag, double* invdiagT,
-                  int has_sub, double sub, int* info, const LaunchCtx& c, PotrfCounters* cnt);
+                  int has_sub, double sub, int* info, const LaunchCtx& c, PotrfCounters* cnt, cudaEvent_t after_first = nullptr,
+                  const std::function<void(int64_t)>* column_done = nullptr);
 // trailing block columns [c0, c1) (rows >= c0: the trapezoid on/below the diagonal) -= P P^T, P = block columns [J, Jend)
 void trailing_update(double* A, int64_t lda, int64_t np, int64_t J, int64_t Jend, int64_t c0, int64_t c1,
                      const LaunchCtx& c, PotrfCounters* cnt);
+
+void trailing_update_cols(double* A, int64_t lda, int64_t np, int64_t J, int64_t Jend, int64_t c0, int64_t c1,
+                          const LaunchCtx& c, PotrfCounters* cnt);
 
 // `la` (optional): a second, high-priority stream and two events for the one-panel look-ahead schedule; null => everything
 // runs on st.st in program order.
 struct PotrfLookahead {
     cudaStream_t panel;
     cudaEvent_t ev_panel, ev_trail;
+    cudaStream_t side;   // optional: the look-ahead update of the next panel's block columns 1.. runs here, concurrently with
+    cudaEvent_t ev_side; //           the factorisation of its block column 0 on `panel`
 };
 void potrf_lower(double* A, int64_t lda, int64_t np, int64_t jb_begin, double* invdiag, double* invdiagT, int has_sub,
                  double sub, int* info, const LaunchCtx& st, const PotrfLookahead* la, PotrfCounters* cnt);

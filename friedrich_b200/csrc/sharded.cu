@@ -17,6 +17,7 @@
 #include "sharded.cuh"
 
 #include <algorithm>
+#include <functional>
 #include <string>
 
 #include "covariance.cuh"
@@ -89,21 +90,61 @@ int factor_sharded(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& 
         const int64_t rows = np - J * TILE, w = (Jend - J) * TILE;
         const int owner = shard_owner(p, P);
         double* buf = cm->pbuf[p & 1].p;
-        if (p >= 2) CU(m, cudaStreamWaitEvent(m->st2, cm->ev_trail[p & 1], 0));
-        if (owner == r) {
-            if (p >= 1) {
-                const int64_t Jp = (p - 1) * PANEL_TILES;
-                update_from_buffer(m, cm->pbuf[(p - 1) & 1].p, Jp, J, J, Jend, pc, &cnt);
+        if (p >= 2) {  // the trailing update with panel p-2 has left this buffer and reached this panel's columns
+            CU(m, cudaStreamWaitEvent(m->st2, cm->ev_trail[p & 1], 0));
+            CU(m, cudaStreamWaitEvent(cm->st_comm, cm->ev_trail[p & 1], 0));
+        }
+        // The panel travels slab by slab (one 128-column block each): as soon as the owner has finalised a block column it
+        // is packed into the contiguous panel buffer and broadcast on the comm stream, while the panel stream factors the
+        // next block column — only the last slab's transfer is on the critical path.
+        int rc_ship = FGP_OK;
+        auto ship = [&](int64_t j, bool is_owner) {
+            double* slab = buf + (j - J) * TILE * rows;
+            if (is_owner) {
+                cudaEventRecord(cm->ev_col, m->st2);
+                cudaStreamWaitEvent(cm->st_comm, cm->ev_col, 0);
+                cudaMemcpy2DAsync(slab, rows * sizeof(double), m->L.p + J * TILE + j * TILE * m->cap, m->cap * sizeof(double),
+                                  rows * sizeof(double), TILE, cudaMemcpyDeviceToDevice, cm->st_comm);
             }
-            factor_panel(m->L.p, m->cap, np, J, Jend, m->inv.p, m->invT.p, has_eps, eps, m->info_d, pc, &cnt);
-            CU(m, cudaMemcpy2DAsync(buf, rows * sizeof(double), m->L.p + J * TILE + J * TILE * m->cap,
-                                    m->cap * sizeof(double), rows * sizeof(double), w, cudaMemcpyDeviceToDevice, m->st2));
+            if (P > 1) {
+                // profiled (class "other") only on the owner: there the duration is the send itself, elsewhere it includes
+                // the wait for the owner's factorisation; the "flops" slot carries the bytes
+                LaunchCtx bc = mc;
+                bc.st = cm->st_comm;
+                if (!is_owner) bc.prof = nullptr;
+                ProfScope ps(bc, PROF_OTHER, (double)rows * TILE * sizeof(double));
+                if (nccl->Broadcast(slab, slab, (size_t)rows * TILE, ncclDouble, owner, cm->comm, cm->st_comm) != ncclSuccess)
+                    rc_ship = FGP_ERR_COMM;
+                cm->bcast_bytes += (double)rows * TILE * sizeof(double);
+            }
+        };
+        if (owner == r) {
+            const std::function<void(int64_t)> on_col = [&](int64_t j) { ship(j, true); };
+            if (p >= 1 && Jend - J > 1) {
+                // look-ahead update by the previous panel: block column 0 here (its factorisation follows at once), block
+                // columns 1.. on the side stream, joined before the panel stream touches block column 1
+                const int64_t Jp = (p - 1) * PANEL_TILES;
+                LaunchCtx sc = mc;
+                sc.st = m->st3;
+                CU(m, cudaEventRecord(m->evC, m->st2));
+                CU(m, cudaStreamWaitEvent(m->st3, m->evC, 0));
+                update_from_buffer(m, cm->pbuf[(p - 1) & 1].p, Jp, J, J, J + 1, pc, &cnt);
+                update_from_buffer(m, cm->pbuf[(p - 1) & 1].p, Jp, J, J + 1, Jend, sc, &cnt);
+                CU(m, cudaEventRecord(m->evC, m->st3));
+                factor_panel(m->L.p, m->cap, np, J, Jend, m->inv.p, m->invT.p, has_eps, eps, m->info_d, pc, &cnt, m->evC, &on_col);
+            } else {
+                if (p >= 1) {
+                    const int64_t Jp = (p - 1) * PANEL_TILES;
+                    update_from_buffer(m, cm->pbuf[(p - 1) & 1].p, Jp, J, J, Jend, pc, &cnt);
+                }
+                factor_panel(m->L.p, m->cap, np, J, Jend, m->inv.p, m->invT.p, has_eps, eps, m->info_d, pc, &cnt, nullptr, &on_col);
+            }
+        } else {
+            for (int64_t j = J; j < Jend; ++j) ship(j, false);
         }
-        if (P > 1) {
-            NC(m, nccl->Broadcast(buf, buf, (size_t)rows * w, ncclDouble, owner, cm->comm, m->st2));
-            cm->bcast_bytes += (double)rows * w * sizeof(double);
-        }
-        CU(m, cudaEventRecord(cm->ev_bcast, m->st2));
+        if (rc_ship != FGP_OK) return fail(m, FGP_ERR_COMM, "ncclBroadcast of a panel slab failed");
+        CU(m, cudaEventRecord(cm->ev_bcast, cm->st_comm));
+        CU(m, cudaStreamWaitEvent(m->st2, cm->ev_bcast, 0));  // the next owner's look-ahead update reads the buffer on st2
         CU(m, cudaStreamWaitEvent(m->st, cm->ev_bcast, 0));
         {
             // every owned panel c > p, c != p+1 (that one is the owner's look-ahead on the panel stream next iteration),

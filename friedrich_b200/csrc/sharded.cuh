@@ -13,7 +13,9 @@ struct fgp_comm {
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
     fgp::DevBuf pbuf[2];                     // contiguous panel buffers: rows [J*128, np) x panel width, ld = rows
-    cudaEvent_t ev_bcast = nullptr;          // panel J has arrived (recorded on the panel stream)
+    cudaStream_t st_comm = nullptr;          // packs and broadcasts the panel slab by slab while the panel stream factors on
+    cudaEvent_t ev_col = nullptr;            // a block column of the panel is final (recorded on the panel stream)
+    cudaEvent_t ev_bcast = nullptr;          // panel J has arrived (recorded on the comm stream)
     cudaEvent_t ev_trail[2] = {nullptr, nullptr};  // trailing update with panel J done (main stream), index J & 1
     double bcast_bytes = 0.0;                // bytes this rank sent or received in the last sharded factorisation
 };
