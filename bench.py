@@ -43,7 +43,7 @@ WORKLOADS = {
 
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per gemm_nt launch, averaged over the launches of one fit,
 # from the ncu capture named in DESIGN.md "Measurement" (profiles/); None until a capture exists for the workload.
-GEMM_TRAFFIC_BYTES_PER_LAUNCH = {}
+GEMM_TRAFFIC_BYTES_PER_LAUNCH = {"metric": 88.73e6}  # profiles/gemm_dram_fit16k_r01h.csv: 27.95 GB over the 315 launches of one fit
 
 
 def fit_flops(n, d):

@@ -58,8 +58,15 @@ void solve_alpha(fgp_model* m) {
     const int nb = (int)(m->np / TILE);
     int* flags = reinterpret_cast<int*>(m->work.p);  // np doubles of scratch >= 2 nb ints
     cudaMemsetAsync(flags, 0, 2 * (size_t)nb * sizeof(int), m->st);
-    trsv_fwd_wave_kernel<<<nb, TRSV_THREADS, 0, m->st>>>(m->L.p, m->cap, m->inv.p, m->y.p, m->z.p, flags);
-    trsv_adj_wave_kernel<<<nb, TRSV_THREADS, 0, m->st>>>(m->L.p, m->cap, m->invT.p, m->z.p, m->alpha.p, flags + nb, nb);
+    static bool attr_done = false;
+    if (!attr_done) {  // the block's inverse diagonal tile lives in 128 KiB of dynamic shared memory
+        cudaFuncSetAttribute(trsv_fwd_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_WAVE_SMEM);
+        cudaFuncSetAttribute(trsv_adj_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_WAVE_SMEM);
+        attr_done = true;
+    }
+    trsv_fwd_wave_kernel<<<nb, TRSV_THREADS, TRSV_WAVE_SMEM, m->st>>>(m->L.p, m->cap, m->inv.p, m->y.p, m->z.p, flags);
+    trsv_adj_wave_kernel<<<nb, TRSV_THREADS, TRSV_WAVE_SMEM, m->st>>>(m->L.p, m->cap, m->invT.p, m->z.p, m->alpha.p, flags + nb,
+                                                                      nb);
     m->launches += 2;
 }
 

@@ -57,13 +57,16 @@ convert_points_kernel(const double* __restrict__ src, int64_t ld, int64_t n, int
 constexpr int TRSV_THREADS = 512;
 
 // y[r] = sum_c M[r + c*ldm] * xs[c], r < 128, c < 128; thread (r = tid & 127, quarter = tid >> 7) sums 32 columns with 4
-// interleaved accumulators, the quarters are added in order.  Result valid in threads with tid < 128.
-__device__ __forceinline__ double tile_matvec_512(const double* __restrict__ M, int64_t ldm, const double* xs, double* red) {
+// interleaved accumulators, the quarters are added in order.  Result valid in threads with tid < 128.  Split in two so the
+// tile's loads can be issued BEFORE the vector is known (the wavefront solves below):
+__device__ __forceinline__ void tile_load_512(const double* __restrict__ M, int64_t ldm, double (&v)[32]) {
     const int r = threadIdx.x & 127, h = threadIdx.x >> 7;
     const double* p = M + r + (int64_t)(32 * h) * ldm;
-    double v[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) v[c] = __ldcg(p + (int64_t)c * ldm);
+}
+__device__ __forceinline__ double tile_apply_512(const double (&v)[32], const double* xs, double* red) {
+    const int r = threadIdx.x & 127, h = threadIdx.x >> 7;
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
     for (int c = 0; c < 32; c += 4) {
@@ -79,13 +82,35 @@ __device__ __forceinline__ double tile_matvec_512(const double* __restrict__ M, 
     __syncthreads();
     return out;
 }
+// the same product with the 128 x 128 tile resident in shared memory (column-major, ld = 128)
+__device__ __forceinline__ double tile_apply_smem_512(const double* Ms, const double* xs, double* red) {
+    const int r = threadIdx.x & 127, h = threadIdx.x >> 7;
+    const double* p = Ms + r + 32 * h * 128;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+        a0 = fma(p[c * 128], xs[32 * h + c], a0);
+        a1 = fma(p[(c + 1) * 128], xs[32 * h + c + 1], a1);
+        a2 = fma(p[(c + 2) * 128], xs[32 * h + c + 2], a2);
+        a3 = fma(p[(c + 3) * 128], xs[32 * h + c + 3], a3);
+    }
+    red[h * 128 + r] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    double out = 0.0;
+    if (threadIdx.x < 128) out = (red[r] + red[128 + r]) + (red[256 + r] + red[384 + r]);
+    __syncthreads();
+    return out;
+}
 
 // ---- wavefront triangular solves: ONE launch per solve instead of one per block column -------------------------------
 // Block i of the grid owns the 128 unknowns of block row i. It consumes the solution blocks it depends on as their owners
 // publish them (a flag per block in global memory, release/acquire), so the 128-step dependency chain costs a flag
 // round trip per step instead of a kernel launch.  Blocks only ever wait for LOWER block indices, which the hardware
-// dispatches first, so the wait cannot deadlock however many blocks are resident.  The arithmetic (order of the block
-// updates j = 0, 1, ... and the mat-vec reductions) does not depend on the timing: results are deterministic.
+// dispatches first, so the wait cannot deadlock however many blocks are resident.  Everything that does not depend on
+// the awaited block is fetched BEFORE the wait: the block's inverse diagonal tile arrives in shared memory by TMA bulk
+// copies at kernel start, and the L tile of each step is loaded into registers ahead of its flag.  The arithmetic (order
+// of the block updates j = 0, 1, ... and the mat-vec reductions) does not depend on the timing: results are deterministic.
+constexpr int TRSV_WAVE_SMEM = 128 * 128 * 8 + 16;
 __device__ __forceinline__ void wave_wait(const int* flag) {
     if (threadIdx.x == 0) {
         int v;
@@ -100,31 +125,45 @@ __device__ __forceinline__ void wave_publish(int* flag) {
     __syncthreads();
     if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
 }
+// 128 columns x 1 KiB of a contiguous 128 x 128 tile -> shared memory, completion on `bar` (lanes 0..127 of the CTA)
+__device__ __forceinline__ void wave_fetch_tile(double* dst, const double* src, uint64_t* bar) {
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, 128 * 128 * 8);
+    __syncthreads();
+    if (threadIdx.x < 128) tma_load_1d(dst + threadIdx.x * 128, src + threadIdx.x * 128, 1024, bar);
+}
 
 // Forward: L x = b.  x_i = inv_i (b_i - sum_{j<i} L[i,j] x_j)
 static __global__ void __launch_bounds__(TRSV_THREADS)
 trsv_fwd_wave_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ inv, const double* __restrict__ b,
                      double* x, int* flags) {
+    extern __shared__ __align__(128) unsigned char wave_smem[];
+    double* inv_s = reinterpret_cast<double*>(wave_smem);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(wave_smem + 128 * 128 * 8);
     __shared__ double xs[128];
     __shared__ double red[512];
     const int r = threadIdx.x & 127;
     const int i = blockIdx.x;
     const int64_t row0 = (int64_t)i * 128;
-    // the two tiles the LAST step needs (L[i, i-1] and inv_i) can be on their way to L2 long before x_{i-1} exists
-    if (threadIdx.x < 128) l2_prefetch(inv + (int64_t)i * 128 * 128 + (int64_t)threadIdx.x * 128, 1024);
-    else if (threadIdx.x < 256 && i > 0) l2_prefetch(L + row0 + ((int64_t)(i - 1) * 128 + (threadIdx.x - 128)) * ld, 1024);
+    wave_fetch_tile(inv_s, inv + (int64_t)i * 128 * 128, bar);
     double v = 0.0;
     if (threadIdx.x < 128) v = b[row0 + r];
+    double t[32];
     for (int j = 0; j < i; ++j) {
+        tile_load_512(L + row0 + (int64_t)j * 128 * ld, ld, t);  // independent of x_j: in flight while we wait for it
         wave_wait(flags + j);
         if (threadIdx.x < 128) xs[r] = __ldcg(x + (int64_t)j * 128 + r);
         __syncthreads();
-        const double s = tile_matvec_512(L + row0 + (int64_t)j * 128 * ld, ld, xs, red);
-        v -= s;
+        v -= tile_apply_512(t, xs, red);
     }
     if (threadIdx.x < 128) xs[r] = v;
+    mbar_wait(bar, 0);
     __syncthreads();
-    const double s = tile_matvec_512(inv + (int64_t)i * 128 * 128, 128, xs, red);
+    const double s = tile_apply_smem_512(inv_s, xs, red);
     if (threadIdx.x < 128) x[row0 + r] = s;
     wave_publish(flags + i);
 }
@@ -135,24 +174,26 @@ trsv_fwd_wave_kernel(const double* __restrict__ L, int64_t ld, const double* __r
 static __global__ void __launch_bounds__(TRSV_THREADS)
 trsv_adj_wave_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ invT, const double* __restrict__ b,
                      double* x, int* flags, int nb) {
+    extern __shared__ __align__(128) unsigned char wave_smem[];
+    double* inv_s = reinterpret_cast<double*>(wave_smem);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(wave_smem + 128 * 128 * 8);
     __shared__ double xs[128];
     __shared__ double bs[128];
     __shared__ double red[512];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i = nb - 1 - (int)blockIdx.x;
-    if (tid < 128) l2_prefetch(invT + (int64_t)i * 128 * 128 + (int64_t)tid * 128, 1024);
-    else if (tid < 256 && i + 1 < nb) l2_prefetch(L + (int64_t)(i + 1) * 128 + ((int64_t)i * 128 + (tid - 128)) * ld, 1024);
+    wave_fetch_tile(inv_s, invT + (int64_t)i * 128 * 128, bar);
     if (tid < 128) bs[tid] = b[(int64_t)i * 128 + tid];
     for (int j = nb - 1; j > i; --j) {
-        wave_wait(flags + (nb - 1 - j));
-        if (tid < 128) xs[tid] = __ldcg(x + (int64_t)j * 128 + tid);
-        __syncthreads();
         const double* Lp = L + (int64_t)j * 128 + ((int64_t)i * 128 + 8 * warp) * ld + lane;
-        double v[8][4];
+        double v[8][4];  // independent of x_j: in flight while we wait for it
 #pragma unroll
         for (int c = 0; c < 8; ++c)
 #pragma unroll
             for (int k = 0; k < 4; ++k) v[c][k] = __ldcg(Lp + (int64_t)c * ld + 32 * k);
+        wave_wait(flags + (nb - 1 - j));
+        if (tid < 128) xs[tid] = __ldcg(x + (int64_t)j * 128 + tid);
+        __syncthreads();
         const double x0 = xs[lane], x1 = xs[lane + 32], x2 = xs[lane + 64], x3 = xs[lane + 96];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -161,8 +202,9 @@ trsv_adj_wave_kernel(const double* __restrict__ L, int64_t ld, const double* __r
             if (lane == 0) bs[8 * warp + c] -= p;
         }
     }
+    mbar_wait(bar, 0);
     __syncthreads();
-    const double s = tile_matvec_512(invT + (int64_t)i * 128 * 128, 128, bs, red);
+    const double s = tile_apply_smem_512(inv_s, bs, red);
     if (tid < 128) x[(int64_t)i * 128 + tid] = s;
     wave_publish(flags + (nb - 1 - i));
 }

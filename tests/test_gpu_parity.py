@@ -427,3 +427,21 @@ def test_full_size_properties_n16384():
     assert np.abs(Krows @ alpha - y[idx]).max() < 1e-9
     gp._refit()
     assert np.array_equal(np.tril(gp.cholesky_factor()), L)  # deterministic, idempotent
+
+
+def test_wavefront_solves_beyond_one_resident_wave_n24576():
+    """192 block rows > 148 SMs: the flag-synchronised triangular solves (csrc/vector_kernels.cuh) must still terminate and
+    give alpha = K^-1 y when not every block of the grid is resident at once (blocks only wait for lower block indices)."""
+    F, N, O, make_dataset, make_inputs = _mods()
+    n, d = 24576, 8
+    X, y = make_dataset(0x5EED0009, n, d)
+    kern, kd = _kern(F, O, "sqexp", d)
+    gp = F.GaussianProcess(F.ZeroPrior(), kern, 0.1, None, X, y)
+    alpha = np.zeros(n)
+    gp._h.check(N.lib().fgp_download_alpha(gp._h.ptr, N.dptr(alpha)))
+    idx = np.random.default_rng(3).choice(n, 32, replace=False)
+    Krows = O.make_covariance_matrix(kd, X[idx], X)
+    Krows[np.arange(32), idx] += 0.1 ** 2
+    assert np.abs(Krows @ alpha - y[idx]).max() < 1e-9
+    m = gp.predict(X[idx])                       # posterior mean at training points = (K - s^2 I) alpha
+    assert close(m, y[idx] - 0.1 ** 2 * alpha[idx])
