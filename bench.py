@@ -133,7 +133,9 @@ def time_oracle(n, d, q, steps, warmup):
     for _ in range(steps):
         oracle_step(O, kdesc, X, y, Xq)
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    flops = fit_flops(n, d) + (2.0 * predict_flops(n, d, q) if q else 0.0)  # the reference does both triangular solves
+    # the same ALGORITHMIC count as the GPU arm's e2e figure (the reference executes about twice the predict flops: it
+    # re-solves K^-1 K_nq with both triangular factors on every call, mod.rs:235, :298 — that shows up as time, not as work)
+    flops = fit_flops(n, d) + (predict_flops(n, d, q) if q else 0.0)
     return dt, flops
 
 
@@ -263,11 +265,16 @@ def run_ours(args, rank, local_rank, world):
     wall_ms = max_over_ranks(wall_ms)
 
     # ---- profiling pass: same K steps with CUDA events around every launch -------------------------------------------
+    # On one GPU the pass runs the SINGLE-STREAM schedule (look-ahead off): every launch then has the GPU to itself and its
+    # event duration is the kernel's own; with look-ahead on, launches of the two streams share SMs and each one's duration
+    # is inflated by the other's work (the flops and the launches are identical either way, results are bit-identical).
     pms, pfl, pcnt = np.zeros(4), np.zeros(4), np.zeros(4, dtype=np.int64)
     tms, tfl, tcnt = np.zeros(4), np.zeros(4), np.zeros(4, dtype=np.int64)
     prof_dev_ms = 0.0
     if not args.no_profile:
         lib.fgp_set_profiling(h.ptr, 1)
+        if not use_sharded:
+            lib.fgp_set_option(h.ptr, N.FGP_OPT_LOOKAHEAD, 0)
         for _ in range(args.steps):
             refit()
             prof_dev_ms += h.last_device_ms()
@@ -276,7 +283,17 @@ def run_ours(args, rank, local_rank, world):
             tfl += pfl
             tcnt += pcnt
         lib.fgp_set_profiling(h.ptr, 0)
+        if not use_sharded and not args.no_lookahead:
+            lib.fgp_set_option(h.ptr, N.FGP_OPT_LOOKAHEAD, 1)
         barrier()
+    # the dominant launch shape alone, back to back: the first trailing update of this fit (m = n - 512, K = 512, lower)
+    iso = None
+    if rank == 0 and not args.no_profile:
+        ms_i, fl_i = C.c_double(0), C.c_double(0)
+        m_iso = (n // 128) * 128 - 512
+        if m_iso >= 512 and lib.fgp_dbg_gemm_bench(local_rank, m_iso, m_iso, 512, 1, 1, 3, C.byref(ms_i), C.byref(fl_i)) == 0:
+            iso = {"shape": f"C({m_iso}x{m_iso}, lower) -= A A^T, K=512", "ms": ms_i.value,
+                   "tflops": fl_i.value / ms_i.value * 1e-9, "frac": fl_i.value / ms_i.value * 1e-9 / FP64_PEAK_TFLOPS}
 
     # ---- predict throughput, queries resident ------------------------------------------------------------------------
     h.check(lib.fgp_stage_queries(h.ptr, N.dptr(Xq), qr, qr))
@@ -336,10 +353,11 @@ def run_ours(args, rank, local_rank, world):
                      "unit": "TFLOP/s", "frac": (gemm_tflops / FP64_PEAK_TFLOPS) if gemm_tflops else None,
                      "traffic": GEMM_TRAFFIC_BYTES_PER_LAUNCH.get(args.workload) if world == 1 else None,
                      "launches": int(tcnt[0]), "share_of_step": float(tms[0] / max(prof_dev_ms, 1e-9)),
-                     "note": "rank 0; achieved = algorithmic flops of all gemm_nt launches / sum of their CUDA-event "
-                             "durations, from a separate pass of the same steps with per-launch events on (with look-ahead "
-                             "the panel-stream launches overlap the main-stream ones, so share_of_step can exceed 1 and "
-                             "the per-launch rate under-reports the kernel; isolated: profiles/gemm_bench_*.jsonl)",
+                     "note": "rank 0; achieved = algorithmic flops of ALL gemm_nt launches of a fit (from the 56-wave trailing "
+                             "updates down to sub-wave panel products) / sum of their CUDA-event durations, from a separate "
+                             "pass of the same steps with per-launch events on and, on one GPU, the single-stream schedule "
+                             "so launches do not share SMs; `isolated` = the dominant launch shape alone, measured live",
+                     "isolated": iso,
                      "profiled_ms_per_step": prof_dev_ms / args.steps,
                      "peak_source": "fp64 DMMA m8n8k4 register-resident burst measured on this pool "
                                     "(profiles/fp64_peak_r01.jsonl; MEASURED_PEAKS.json has no fp64 figure; nominal "
