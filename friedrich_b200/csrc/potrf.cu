@@ -353,6 +353,7 @@ void trailing_update_cols(double* A, int64_t lda, int64_t np, int64_t J, int64_t
 void potrf_lower(double* A, int64_t lda, int64_t np, int64_t jb_begin, double* invdiag, double* invdiagT, int has_sub,
                  double sub, int* info, const LaunchCtx& st, const PotrfLookahead* la, PotrfCounters* cnt) {
     const int64_t nb = np / TILE;
+    const int64_t PANEL_TILES = panel_tiles(np);
     if (jb_begin >= nb) return;
     if (!la || !la->panel) {
         // single stream, no look-ahead: panel, then the whole trailing update

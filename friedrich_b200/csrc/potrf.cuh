@@ -1,12 +1,12 @@
 // potrf.cuh — blocked lower Cholesky on the padded device matrix (replaces nalgebra Cholesky::new /
 // new_with_substitute called from make_cholesky_cov_matrix, src/algebra/mod.rs:81-91).
 //
-//   for each outer panel of PANEL_TILES block columns:
+//   for each outer panel of panel_tiles(np) block columns:
 //       for each 128-wide block column j of the panel:
 //           A[j:, j] -= A[j:, panel_start:j] * A[j, panel_start:j]^T        gemm_nt  (left-looking inside the panel)
 //           L_jj = chol(A[j, j]),  inv_j = L_jj^-1                           potrf_diag_kernel (one CTA, warp-shuffle pivots)
 //           A[j+1:, j] = A[j+1:, j] * inv_j^T                                gemm_nt  (TRSM as a GEMM, in place)
-//       A[after:, after:] -= P * P^T,  P = A[after:, panel]                  gemm_nt  (SYRK, K = 128*PANEL_TILES)
+//       A[after:, after:] -= P * P^T,  P = A[after:, panel]                  gemm_nt  (SYRK, K = 128*panel_tiles)
 //
 // Failure semantics of the reference are kept: a pivot that is zero, negative or NaN is replaced by the
 // substitute (`cholesky_epsilon`) when one is given and valid, otherwise the (1-based) failing column is
@@ -23,7 +23,10 @@ namespace fgp {
 constexpr int DIAG_DS = 129;                                   // smem row stride of the 128x128 diagonal tile
 constexpr int DIAG_THREADS = 512;
 constexpr int DIAG_SMEM_BYTES = (128 * DIAG_DS + 96 * 33 + 128) * 8;
-constexpr int PANEL_TILES = 4;                                 // outer panel = 512 columns
+// Outer panel width in 128-column tiles: 512 columns, 1024 from n = 24576 on. A wider panel runs the trailing update at the
+// GEMM kernel's better depth (K = 1024: 35.1 vs 34.3 TF/s) and halves its C traffic, but lengthens the serial panel chain,
+// which only large problems hide: measured n = 32768 360 -> 352 ms, n = 16384 50.3 -> 50.7 ms with 8 tiles.
+inline int panel_tiles(int64_t np) { return np >= 24576 ? 8 : 4; }
 
 struct PotrfCounters {
     int64_t launches = 0;
