@@ -290,7 +290,7 @@ def run_ours(args, rank, local_rank, world):
     iso = None
     if rank == 0 and not args.no_profile:
         ms_i, fl_i = C.c_double(0), C.c_double(0)
-        k_iso = 1024 if n >= 24576 else 512  # csrc/potrf.cuh panel_tiles(): panel width = depth of the trailing updates
+        k_iso = 1024 if (n >= 24576 and not use_sharded) else 512  # csrc/potrf.cuh panel_tiles(): panel width = update depth
         m_iso = (n // 128) * 128 - k_iso
         if m_iso >= k_iso and lib.fgp_dbg_gemm_bench(local_rank, m_iso, m_iso, k_iso, 1, 1, 3, C.byref(ms_i), C.byref(fl_i)) == 0:
             iso = {"shape": f"C({m_iso}x{m_iso}, lower) -= A A^T, K={k_iso}", "ms": ms_i.value,
@@ -337,7 +337,7 @@ def run_ours(args, rank, local_rank, world):
         "data": "synthetic",
         "config": {"workload": desc, "n": n, "d": d, "q": q, "noise": noise, "kernel": "SquaredExp(ls=sqrt(d/6), ampl=1)",
                    "l2": "inputs larger than L2 (factor = %.2f GB)" % (8.0 * n * n / 1e9),
-                   "multi_gpu": (f"block-cyclic {1024 if n >= 24576 else 512}-column panels, NCCL panel broadcast slab by slab, replicated factor; "
+                   "multi_gpu": ("block-cyclic 512-column panels, NCCL panel broadcast slab by slab, replicated factor; "
                                  "queries sharded") if use_sharded else "single GPU",
                    "lookahead": not args.no_lookahead},
         "frac_of_fp64_peak": value / (world * FP64_PEAK_TFLOPS),

@@ -775,7 +775,7 @@ FGP_EXPORT double fgp_comm_last_bytes(const fgp_model* m) { return (m && m->comm
 FGP_EXPORT int fgp_shard_plan(int64_t n, int nranks, int rank, int64_t* panel_cols, int64_t* n_panels, int64_t* n_owned,
                               double* flop_share) {
     if (n <= 0 || nranks < 1 || rank < 0 || rank >= nranks) return FGP_ERR_BAD_ARG;
-    const int64_t np = round_up(n, TILE), nb = np / TILE, PANEL_TILES = panel_tiles(np), NP = (nb + PANEL_TILES - 1) / PANEL_TILES;
+    const int64_t np = round_up(n, TILE), nb = np / TILE, PANEL_TILES = panel_tiles(np, nranks), NP = (nb + PANEL_TILES - 1) / PANEL_TILES;
     int64_t owned = 0;
     double mine = 0.0, total = 0.0;
     for (int64_t p = 0; p < NP; ++p) {

@@ -23,10 +23,13 @@ namespace fgp {
 constexpr int DIAG_DS = 129;                                   // smem row stride of the 128x128 diagonal tile
 constexpr int DIAG_THREADS = 512;
 constexpr int DIAG_SMEM_BYTES = (128 * DIAG_DS + 96 * 33 + 128) * 8;
-// Outer panel width in 128-column tiles: 512 columns, 1024 from n = 24576 on. A wider panel runs the trailing update at the
-// GEMM kernel's better depth (K = 1024: 35.1 vs 34.3 TF/s) and halves its C traffic, but lengthens the serial panel chain,
-// which only large problems hide: measured n = 32768 360 -> 352 ms, n = 16384 50.3 -> 50.7 ms with 8 tiles.
-inline int panel_tiles(int64_t np) { return np >= 24576 ? 8 : 4; }
+// Outer panel width in 128-column tiles: 512 columns; 1024 from n = 24576 on when ONE GPU factors the matrix. A wider panel
+// runs the trailing update at the GEMM kernel's better depth (K = 1024: 35.3 vs 34.4 TF/s) and halves its C traffic, but
+// lengthens the serial panel chain, which only large single-GPU problems hide: measured n = 32768 360 -> 352 ms, n = 16384
+// 50.3 -> 50.7 ms, and on 8 GPUs n = 32768 86 -> 102 ms (the chain is what bounds the sharded fit, and the block-cyclic
+// balance coarsens), so the sharded schedule keeps 512. (A multi-GPU factor therefore equals the single-GPU one bit for bit
+// below n = 24576 and to rounding, ~1e-14 normwise, above.)
+inline int panel_tiles(int64_t np, int nranks = 1) { return (nranks == 1 && np >= 24576) ? 8 : 4; }
 
 struct PotrfCounters {
     int64_t launches = 0;

@@ -56,7 +56,7 @@ int factor_sharded(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& 
     const int P = cm->nranks, r = cm->rank;
     const NcclApi* nccl = nccl_api();
     if (P > 1 && !nccl) return fail(m, FGP_ERR_COMM, "libnccl.so.2 could not be loaded");
-    const int64_t np = m->np, nb = np / TILE, PANEL_TILES = panel_tiles(np), NP = (nb + PANEL_TILES - 1) / PANEL_TILES;
+    const int64_t np = m->np, nb = np / TILE, PANEL_TILES = panel_tiles(np, P), NP = (nb + PANEL_TILES - 1) / PANEL_TILES;
     const int64_t W = (int64_t)PANEL_TILES * TILE;
     CU(m, cm->pbuf[0].reserve((size_t)np * W));
     CU(m, cm->pbuf[1].reserve((size_t)np * W));
