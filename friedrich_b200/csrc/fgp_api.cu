@@ -91,11 +91,25 @@ int reserve_training(fgp_model* m, int64_t cap_rows, int64_t dp, bool keep) {
 int factor_resident(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& kt, double noise, int has_eps,
                     double eps) {
     CU(m, cudaMemsetAsync(m->info_d, 0, sizeof(int), m->st));
-    write_covariance(m, kt, kd, train_pair_args(m), m->L.p, m->cap, m->n, m->n, noise * noise);
+    // Gram: the first panel's block columns first; the columns behind it are assembled on the main stream WHILE the panel
+    // stream already factors the first panel (potrf_lower's hook)
+    const int64_t nb = m->np / TILE, pt = std::min<int64_t>(panel_tiles(m->np), nb);
+    PairArgs pa0 = train_pair_args(m);
+    pa0.col_tile0 = 0;
+    pa0.col_tiles = (int)(pt * TILE / PAIR_TN);
+    write_covariance(m, kt, kd, pa0, m->L.p, m->cap, m->n, m->n, noise * noise);
+    const std::function<void()> rest = [&]() {
+        if (pt >= nb) return;
+        PairArgs pa1 = train_pair_args(m);
+        pa1.row_tile0 = (int)pt;  // rows above the first remaining diagonal tile are in the upper triangle
+        pa1.col_tile0 = (int)(pt * TILE / PAIR_TN);
+        pa1.col_tiles = (int)((nb - pt) * TILE / PAIR_TN);
+        write_covariance(m, kt, kd, pa1, m->L.p, m->cap, m->n, m->n, noise * noise);
+    };
     PotrfCounters cnt;
     const PotrfLookahead la{m->st2, m->evA, m->evB, m->st3, m->evC};
     potrf_lower(m->L.p, m->cap, m->np, 0, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->ctx(), m->lookahead ? &la : nullptr,
-                &cnt);
+                &cnt, &rest);
     m->launches += cnt.launches;
     CU(m, cudaMemcpyAsync(m->info_h, m->info_d, sizeof(int), cudaMemcpyDeviceToHost, m->st));
     solve_alpha(m);

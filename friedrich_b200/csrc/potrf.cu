@@ -351,11 +351,16 @@ void trailing_update_cols(double* A, int64_t lda, int64_t np, int64_t J, int64_t
 }
 
 void potrf_lower(double* A, int64_t lda, int64_t np, int64_t jb_begin, double* invdiag, double* invdiagT, int has_sub,
-                 double sub, int* info, const LaunchCtx& st, const PotrfLookahead* la, PotrfCounters* cnt) {
+                 double sub, int* info, const LaunchCtx& st, const PotrfLookahead* la, PotrfCounters* cnt,
+                 const std::function<void()>* after_first_panel_may_start) {
     const int64_t nb = np / TILE;
     const int64_t PANEL_TILES = panel_tiles(np);
-    if (jb_begin >= nb) return;
+    if (jb_begin >= nb) {
+        if (after_first_panel_may_start) (*after_first_panel_may_start)();
+        return;
+    }
     if (!la || !la->panel) {
+        if (after_first_panel_may_start) (*after_first_panel_may_start)();
         // single stream, no look-ahead: panel, then the whole trailing update
         for (int64_t J = jb_begin; J < nb; J += PANEL_TILES) {
             const int64_t Jend = (J + PANEL_TILES < nb) ? J + PANEL_TILES : nb;
@@ -376,6 +381,11 @@ void potrf_lower(double* A, int64_t lda, int64_t np, int64_t jb_begin, double* i
     factor_panel(A, lda, np, J, Jend, invdiag, invdiagT, has_sub, sub, info, pc, cnt);
     cudaEventRecord(la->ev_panel, la->panel);
     bool first = true;
+    if (after_first_panel_may_start) {
+        (*after_first_panel_may_start)();       // M: e.g. the Gram columns behind the first panel, while P factors it
+        cudaEventRecord(la->ev_trail, st.st);   // ... which P must see before its first look-ahead update
+        first = false;
+    }
     while (Jend < nb) {
         const int64_t Jend2 = (Jend + PANEL_TILES < nb) ? Jend + PANEL_TILES : nb;
         cudaStreamWaitEvent(st.st, la->ev_panel, 0);                   // M: panel [J, Jend) is final

@@ -63,7 +63,11 @@ struct PotrfLookahead {
     cudaStream_t side;   // optional: the look-ahead update of the next panel's block columns 1.. runs here, concurrently with
     cudaEvent_t ev_side; //           the factorisation of its block column 0 on `panel`
 };
+// `after_first_panel_may_start` (optional, look-ahead schedule only): called on the host once the panel stream has been
+// released to factor the first panel; whatever it enqueues on st.st (the Gram assembly of the columns BEHIND the first
+// panel) runs concurrently with that factorisation and is waited for before anything else touches those columns.
 void potrf_lower(double* A, int64_t lda, int64_t np, int64_t jb_begin, double* invdiag, double* invdiagT, int has_sub,
-                 double sub, int* info, const LaunchCtx& st, const PotrfLookahead* la, PotrfCounters* cnt);
+                 double sub, int* info, const LaunchCtx& st, const PotrfLookahead* la, PotrfCounters* cnt,
+                 const std::function<void()>* after_first_panel_may_start = nullptr);
 
 }  // namespace fgp
