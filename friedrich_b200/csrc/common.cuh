@@ -1,8 +1,9 @@
 // common.cuh — shared device helpers for libfgp_sm100 (sm_100a only).
 //
 // fp64 tensor path: there is no tcgen05 `.kind::f64` (ptxas rejects it); the fp64 tensor pipe of
-// B200 is reached with `mma.sync.aligned.m8n8k4.f64` -> SASS DMMA.8x8x4.  Operand staging uses the TMA engine
-// (`cp.async.bulk` -> SASS UBLKCP) completing on mbarriers.
+// B200 is reached with `mma.sync.aligned.m8n8k4.f64` -> SASS DMMA.8x8x4.  Tiles move through the TMA engine: tensor copies
+// (`cp.async.bulk.tensor.2d` -> UTMALDG / UTMASTG, and `cp.reduce.async.bulk.tensor` -> UTMAREDG for C += tile at the L2),
+// 1-D bulk copies (`cp.async.bulk` -> UBLKCP) and L2 prefetches, completing on mbarriers / bulk groups.
 #pragma once
 
 #include <cuda_runtime.h>

@@ -4,9 +4,13 @@
 //   for each outer panel of panel_tiles(np) block columns:
 //       for each 128-wide block column j of the panel:
 //           A[j:, j] -= A[j:, panel_start:j] * A[j, panel_start:j]^T        gemm_nt  (left-looking inside the panel)
-//           L_jj = chol(A[j, j]),  inv_j = L_jj^-1                           potrf_diag_kernel (one CTA, warp-shuffle pivots)
+//           L_jj = chol(A[j, j]),  inv_j = L_jj^-1                           potrf_diag_kernel (one CTA, see potrf.cu)
 //           A[j+1:, j] = A[j+1:, j] * inv_j^T                                gemm_nt  (TRSM as a GEMM, in place)
 //       A[after:, after:] -= P * P^T,  P = A[after:, panel]                  gemm_nt  (SYRK, K = 128*panel_tiles)
+//
+// Schedule (potrf_lower): one-panel look-ahead — the next panel is updated and factored on a high-priority stream while the
+// main stream applies the current panel to everything behind it; the look-ahead update itself is split over a third
+// stream so that the next panel's first diagonal tile can start as soon as ITS block column is up to date.
 //
 // Failure semantics of the reference are kept: a pivot that is zero, negative or NaN is replaced by the
 // substitute (`cholesky_epsilon`) when one is given and valid, otherwise the (1-based) failing column is
