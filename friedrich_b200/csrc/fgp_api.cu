@@ -107,7 +107,7 @@ int factor_resident(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits&
         write_covariance(m, kt, kd, pa1, m->L.p, m->cap, m->n, m->n, noise * noise);
     };
     PotrfCounters cnt;
-    const PotrfLookahead la{m->st2, m->evA, m->evB, m->st3, m->evC};
+    const PotrfLookahead la{m->st2, m->evA, m->evB, m->st3, m->evC, m->evD};
     potrf_lower(m->L.p, m->cap, m->np, 0, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->ctx(), m->lookahead ? &la : nullptr,
                 &cnt, &rest);
     m->launches += cnt.launches;
@@ -276,6 +276,7 @@ FGP_EXPORT int fgp_create(int device, fgp_model** out) {
               cudaStreamCreateWithPriority(&m->st2, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
               cudaStreamCreateWithPriority(&m->st3, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
               cudaEventCreateWithFlags(&m->evC, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&m->evD, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreate(&m->ev0) == cudaSuccess && cudaEventCreate(&m->ev1) == cudaSuccess &&
               cudaEventCreateWithFlags(&m->evA, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&m->evB, cudaEventDisableTiming) == cudaSuccess &&
@@ -310,6 +311,7 @@ FGP_EXPORT int fgp_destroy(fgp_model* m) {
         if (m->evA) cudaEventDestroy(m->evA);
         if (m->evB) cudaEventDestroy(m->evB);
         if (m->evC) cudaEventDestroy(m->evC);
+        if (m->evD) cudaEventDestroy(m->evD);
         m->prof.destroy();
         if (m->st) cudaStreamDestroy(m->st);
         if (m->st2) cudaStreamDestroy(m->st2);
@@ -665,7 +667,7 @@ FGP_EXPORT int fgp_add_samples(fgp_model* m, const double* Xnew, int64_t ldx, in
     m->launches += trsm_fwd_t(Arows, m->cap, np_new - jb * TILE, m->L.p, m->cap, m->inv.p, 0, jb, Arows + jb * TILE * m->cap,
                               m->ctx());
     PotrfCounters cnt;
-    const PotrfLookahead la{m->st2, m->evA, m->evB, m->st3, m->evC};
+    const PotrfLookahead la{m->st2, m->evA, m->evB, m->st3, m->evC, m->evD};
     potrf_lower(m->L.p, m->cap, np_new, jb, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->ctx(), m->lookahead ? &la : nullptr,
                 &cnt);
     m->launches += cnt.launches;

@@ -51,7 +51,7 @@ struct fgp_model {
     cudaStream_t st2 = nullptr;  // look-ahead / copy stream
     cudaStream_t st3 = nullptr;  // side stream of the look-ahead: the next panel's block columns 1.. are updated here while
                                  // block column 0 is already being factored on st2
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr, evC = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr, evC = nullptr, evD = nullptr;
     std::mutex mu;
     std::string err;
 

@@ -295,21 +295,11 @@ cudaError_t potrf_prepare() {
 
 // block columns [J, Jend) of one panel, left-looking inside the panel; every launch goes to c.st
 void factor_panel(double* A, int64_t lda, int64_t np, int64_t J, int64_t Jend, double* invdiag, double* invdiagT,
-                         int has_sub, double sub, int* info, const LaunchCtx& c, PotrfCounters* cnt, cudaEvent_t after_first,
+                         int has_sub, double sub, int* info, const LaunchCtx& c, PotrfCounters* cnt, const PanelSide* side,
                          const std::function<void(int64_t)>* column_done) {
     const int64_t nb = np / TILE;
     for (int64_t j = J; j < Jend; ++j) {
         double* Ajj = A + j * TILE + j * TILE * lda;
-        if (j == J + 1 && after_first) cudaStreamWaitEvent(c.st, after_first, 0);
-        if (j > J) {
-            GemmArgs g{};
-            g.C = Ajj; g.ldc = lda;
-            g.A = A + j * TILE + J * TILE * lda; g.lda = lda;
-            g.B = g.A; g.ldb = lda;
-            g.M = (int)(np - j * TILE); g.N = TILE; g.K = (int)((j - J) * TILE);
-            g.alpha = -1.0; g.beta_one = 1; g.lower = 0; g.k_from_tile = 0;
-            cnt->launches += gemm_nt_launch(g, c) > 0;
-        }
         {
             ProfScope ps(c, PROF_POTRF_DIAG, 128.0 * 128.0 * 128.0 / 3.0);
             potrf_diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM_BYTES, c.st>>>(Ajj, lda, invdiag + j * TILE * TILE,
@@ -327,6 +317,23 @@ void factor_panel(double* A, int64_t lda, int64_t np, int64_t J, int64_t Jend, d
             cnt->launches += gemm_nt_launch(g, c) > 0;
         }
         if (column_done) (*column_done)(j);
+        if (j + 1 < Jend) {
+            // rank-128 update of the panel's remaining block columns by block column j
+            if (side && side->st) {
+                LaunchCtx sc = c;
+                sc.st = side->st;
+                cudaEventRecord(side->ev_fork, c.st);            // block column j is final
+                cudaStreamWaitEvent(c.st, side->ev_join, 0);     // the side stream's earlier work on block column j+1 is done
+                trailing_update(A, lda, np, j, j + 1, j + 1, j + 2, c, cnt);
+                if (j + 2 < Jend) {
+                    cudaStreamWaitEvent(side->st, side->ev_fork, 0);
+                    trailing_update(A, lda, np, j, j + 1, j + 2, Jend, sc, cnt);
+                    cudaEventRecord(side->ev_join, side->st);
+                }
+            } else {
+                trailing_update(A, lda, np, j, j + 1, j + 1, Jend, c, cnt);
+            }
+        }
     }
 }
 
@@ -378,7 +385,11 @@ void potrf_lower(double* A, int64_t lda, int64_t np, int64_t jb_begin, double* i
     cudaStreamWaitEvent(la->panel, la->ev_trail, 0);
     int64_t J = jb_begin;
     int64_t Jend = (J + PANEL_TILES < nb) ? J + PANEL_TILES : nb;
-    factor_panel(A, lda, np, J, Jend, invdiag, invdiagT, has_sub, sub, info, pc, cnt);
+    {
+        // the first panel: nothing has run on the side stream for it, ev_side carries an old (completed) record at most
+        const PanelSide ps{la->side, la->ev_fork, la->ev_side};
+        factor_panel(A, lda, np, J, Jend, invdiag, invdiagT, has_sub, sub, info, pc, cnt, la->side ? &ps : nullptr);
+    }
     cudaEventRecord(la->ev_panel, la->panel);
     bool first = true;
     if (after_first_panel_may_start) {
@@ -400,7 +411,8 @@ void potrf_lower(double* A, int64_t lda, int64_t np, int64_t jb_begin, double* i
             trailing_update(A, lda, np, J, Jend, Jend, Jend + 1, pc, cnt);
             trailing_update_cols(A, lda, np, J, Jend, Jend + 1, Jend2, sc, cnt);
             cudaEventRecord(la->ev_side, la->side);
-            factor_panel(A, lda, np, Jend, Jend2, invdiag, invdiagT, has_sub, sub, info, pc, cnt, la->ev_side);
+            const PanelSide ps{la->side, la->ev_fork, la->ev_side};
+            factor_panel(A, lda, np, Jend, Jend2, invdiag, invdiagT, has_sub, sub, info, pc, cnt, &ps);
         } else {
             trailing_update(A, lda, np, J, Jend, Jend, Jend2, pc, cnt);    // look-ahead columns
             factor_panel(A, lda, np, Jend, Jend2, invdiag, invdiagT, has_sub, sub, info, pc, cnt);

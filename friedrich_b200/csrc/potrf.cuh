@@ -3,9 +3,9 @@
 //
 //   for each outer panel of panel_tiles(np) block columns:
 //       for each 128-wide block column j of the panel:
-//           A[j:, j] -= A[j:, panel_start:j] * A[j, panel_start:j]^T        gemm_nt  (left-looking inside the panel)
 //           L_jj = chol(A[j, j]),  inv_j = L_jj^-1                           potrf_diag_kernel (one CTA, see potrf.cu)
 //           A[j+1:, j] = A[j+1:, j] * inv_j^T                                gemm_nt  (TRSM as a GEMM, in place)
+//           A[c:, c] -= A[c:, j] * A[c, j]^T  for the panel's columns c > j   gemm_nt  (right-looking inside the panel, K = 128)
 //       A[after:, after:] -= P * P^T,  P = A[after:, panel]                  gemm_nt  (SYRK, K = 128*panel_tiles)
 //
 // Schedule (potrf_lower): one-panel look-ahead — the next panel is updated and factored on a high-priority stream while the
@@ -45,12 +45,20 @@ cudaError_t potrf_prepare();
 // jb_begin must already hold final factor values in ALL rows (used by add_samples: the caller has applied them to
 // the trailing block). invdiag / invdiagT: [np/128][128*128] (inverse blocks and their transposes). info: device int, 0 on entry.
 // block columns [J, Jend) of one panel (left-looking inside the panel: update, diagonal tile, panel solve); launches on c.st
-// `after_first` (optional): an event the stream waits for after block column J has been factored and solved, before block
-// column J+1 is touched (the look-ahead's side-stream update of block columns J+1.. by the previous panel).
+// Inside the panel the factorisation is right-looking in rank-128 steps: after block column j is final, the panel's remaining
+// block columns get -= L[:, j] L[cols, j]^T. With a `side` stream only block column j+1 — the one the next diagonal tile waits
+// for — is updated on c.st; block columns j+2.. are updated on the side stream, concurrently with that diagonal tile.
+// `side->ev_join` must carry the side stream's last work on this panel's columns (the look-ahead update of block columns
+// J+1.. by the previous panel) — c.st waits for it before it touches block column J+1. Every tile receives the same rank-128
+// updates in the same order with or without a side stream, so the results are identical.
 // `column_done` (optional): called on the host right after the launches that finalise block column j (diagonal tile + panel
 // solve) have been enqueued on c.st — the sharded fit ships the column to the other GPUs from there.
+struct PanelSide {
+    cudaStream_t st;
+    cudaEvent_t ev_fork, ev_join;
+};
 void factor_panel(double* A, int64_t lda, int64_t np, int64_t J, int64_t Jend, double* invdiag, double* invdiagT,
-                  int has_sub, double sub, int* info, const LaunchCtx& c, PotrfCounters* cnt, cudaEvent_t after_first = nullptr,
+                  int has_sub, double sub, int* info, const LaunchCtx& c, PotrfCounters* cnt, const PanelSide* side = nullptr,
                   const std::function<void(int64_t)>* column_done = nullptr);
 // trailing block columns [c0, c1) (rows >= c0: the trapezoid on/below the diagonal) -= P P^T, P = block columns [J, Jend)
 void trailing_update(double* A, int64_t lda, int64_t np, int64_t J, int64_t Jend, int64_t c0, int64_t c1,
@@ -65,7 +73,8 @@ struct PotrfLookahead {
     cudaStream_t panel;
     cudaEvent_t ev_panel, ev_trail;
     cudaStream_t side;   // optional: the look-ahead update of the next panel's block columns 1.. runs here, concurrently with
-    cudaEvent_t ev_side; //           the factorisation of its block column 0 on `panel`
+    cudaEvent_t ev_side; //           the factorisation of its block column 0 on `panel`; also the in-panel side updates
+    cudaEvent_t ev_fork; //           (factor_panel's PanelSide = {side, ev_fork, ev_side})
 };
 // `after_first_panel_may_start` (optional, look-ahead schedule only): called on the host once the panel stream has been
 // released to factor the first panel; whatever it enqueues on st.st (the Gram assembly of the columns BEHIND the first

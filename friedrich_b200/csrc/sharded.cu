@@ -131,13 +131,15 @@ int factor_sharded(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& 
                 update_from_buffer(m, cm->pbuf[(p - 1) & 1].p, Jp, J, J, J + 1, pc, &cnt);
                 update_from_buffer(m, cm->pbuf[(p - 1) & 1].p, Jp, J, J + 1, Jend, sc, &cnt);
                 CU(m, cudaEventRecord(m->evC, m->st3));
-                factor_panel(m->L.p, m->cap, np, J, Jend, m->inv.p, m->invT.p, has_eps, eps, m->info_d, pc, &cnt, m->evC, &on_col);
+                const PanelSide ps{m->st3, m->evD, m->evC};
+                factor_panel(m->L.p, m->cap, np, J, Jend, m->inv.p, m->invT.p, has_eps, eps, m->info_d, pc, &cnt, &ps, &on_col);
             } else {
                 if (p >= 1) {
                     const int64_t Jp = (p - 1) * PANEL_TILES;
                     update_from_buffer(m, cm->pbuf[(p - 1) & 1].p, Jp, J, J, Jend, pc, &cnt);
                 }
-                factor_panel(m->L.p, m->cap, np, J, Jend, m->inv.p, m->invT.p, has_eps, eps, m->info_d, pc, &cnt, nullptr, &on_col);
+                const PanelSide ps{m->st3, m->evD, m->evC};  // evC: at most an old, completed record (nothing ran on st3 for it)
+                factor_panel(m->L.p, m->cap, np, J, Jend, m->inv.p, m->invT.p, has_eps, eps, m->info_d, pc, &cnt, &ps, &on_col);
             }
         } else {
             for (int64_t j = J; j < Jend; ++j) ship(j, false);
