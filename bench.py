@@ -305,6 +305,14 @@ def run_ours(args, rank, local_rank, world):
         predict_staged()
         pred_ms += h.last_device_ms()
     pred_ms = max_over_ranks(pred_ms / args.steps)
+    # single-query latency (mean + variance of ONE staged query; the wavefront-solve path of csrc/fgp_api.cu predict_small)
+    h.check(lib.fgp_stage_queries(h.ptr, N.dptr(Xq), qr, 1))
+    q1_ms = []
+    for _ in range(args.warmup + args.steps):
+        predict_staged()
+        q1_ms.append(h.last_device_ms())
+    q1_ms = float(np.median(q1_ms[args.warmup:]))
+    h.check(lib.fgp_stage_queries(h.ptr, N.dptr(Xq), qr, qr))
 
     # ---- timed region 2: end to end through the C-ABI with host buffers -------------------------------------------------
     for _ in range(max(1, args.warmup // 2)):
@@ -341,7 +349,7 @@ def run_ours(args, rank, local_rank, world):
                                  "queries sharded") if use_sharded else "single GPU",
                    "lookahead": not args.no_lookahead},
         "frac_of_fp64_peak": value / (world * FP64_PEAK_TFLOPS),
-        "predict_qps": q / (pred_ms * 1e-3), "predict_ms": pred_ms,
+        "predict_qps": q / (pred_ms * 1e-3), "predict_ms": pred_ms, "predict_q1_latency_ms": q1_ms,
         "wall_ms_per_step": wall_ms / args.steps,
         "e2e": {"value": (fit_flops(n, d) + world * predict_flops(n, d, qr)) / (e2e_ms * 1e-3) * 1e-12, "unit": "TFLOP/s",
                 "ms_per_step": e2e_ms, "fit_ms": e2e_fit_ms / args.steps,

@@ -142,7 +142,7 @@ int stage_queries(fgp_model* m, const double* Xq, int64_t ldq, int64_t q) {
     CU(m, m->qnc.reserve((size_t)qp));
     CU(m, m->qnr.reserve((size_t)qp));
     CU(m, m->bt.reserve((size_t)qp * m->np));
-    CU(m, m->partial.reserve((size_t)(m->np / ROWRED_CHUNK) * qp));
+    CU(m, m->partial.reserve((size_t)std::max<int64_t>(m->np / ROWRED_CHUNK, 2) * qp));
     CU(m, m->mean_d.reserve((size_t)qp));
     CU(m, m->var_d.reserve((size_t)qp));
     convert_points_kernel<<<(unsigned)((qp + 255) / 256), 256, 0, m->st>>>(m->staging.p, q, q, (int)m->d, (int)m->dp,
@@ -176,8 +176,47 @@ PairArgs query_pair_args(const fgp_model* m) {
 //   mean = Bt * alpha                                   == (K^-1 K_nq)^T y  (mod.rs:235,241) with alpha = K^-1 y cached
 //   Bt <- Bt * L^-T                                     l().solve_lower_triangular (mod.rs:260-263), transposed
 //   var_i = k(q_i,q_i) - || Bt[i,:] ||^2                mod.rs:266-270
+// Latency path for a handful of queries (the Bayesian-optimisation use case: one candidate at a time): the 128-step chain of
+// the multi-RHS solve costs ~10 ms however few right-hand sides there are, a wavefront forward substitution per query 0.4 ms.
+//   Kc (np x q, one query per COLUMN) = k(train, query);  mean_i = Kc[:, i] . alpha;  z_i = L^-1 Kc[:, i] in place;
+//   var_i = k(q_i, q_i) - ||z_i||^2                                                            (mod.rs:235-241, :260-270)
+constexpr int64_t PREDICT_SMALL_Q = 16;
+int predict_small(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& kt, int want_mean, int want_var) {
+    const int64_t qp = m->qp, np = m->np, q = m->q;
+    const int nb = (int)(np / TILE);
+    PairArgs pa{};
+    pa.xa_c = m->xc.p; pa.xa_r = m->xr.p; pa.na = m->nc.p;     // rows: training points
+    pa.xb_c = m->qc.p; pa.xb_r = m->qr.p; pa.nb = m->qnc.p;    // columns: queries
+    pa.dp = (int)m->dp;
+    pa.rows = np;
+    pa.cols = qp;
+    pa.symmetric = 0;
+    double* Kc = m->bt.p;  // np x qp, ld = np (the buffer holds qp x np doubles)
+    write_covariance(m, kt, kd, pa, Kc, np, m->n, q, 0.0);
+    const DevKernel dk = to_dev(kd);
+    if (want_mean) {
+        col_reduce_kernel<0><<<(unsigned)q, 256, 0, m->st>>>(Kc, np, m->alpha.p, np, m->partial.p);
+        rowreduce_final_kernel<<<(unsigned)(qp / 128), 128, 0, m->st>>>(m->partial.p, 1, qp, q, 0, dk, m->qnr.p, m->mean_d.p);
+        m->launches += 2;
+        m->have_mean = true;
+    }
+    if (want_var) {
+        int* flags = reinterpret_cast<int*>(m->work.p);  // np doubles of scratch >= q * nb ints for q <= 16
+        CU(m, cudaMemsetAsync(flags, 0, (size_t)q * nb * sizeof(int), m->st));
+        for (int64_t i = 0; i < q; ++i)
+            trsv_fwd_wave_kernel<<<nb, TRSV_THREADS, TRSV_WAVE_SMEM, m->st>>>(m->L.p, m->cap, m->inv.p, Kc + i * np, Kc + i * np,
+                                                                            flags + i * nb);
+        col_reduce_kernel<1><<<(unsigned)q, 256, 0, m->st>>>(Kc, np, nullptr, np, m->partial.p + qp);
+        rowreduce_final_kernel<<<(unsigned)(qp / 128), 128, 0, m->st>>>(m->partial.p + qp, 1, qp, q, 1, dk, m->qnr.p, m->var_d.p);
+        m->launches += q + 2;
+        m->have_var = true;
+    }
+    return FGP_OK;
+}
+
 int predict_device(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& kt, int want_mean, int want_var) {
     const int64_t qp = m->qp, np = m->np;
+    if (want_var && m->q <= PREDICT_SMALL_Q && !m->force_batched_predict) return predict_small(m, kd, kt, want_mean, want_var);
     write_covariance(m, kt, kd, query_pair_args(m), m->bt.p, qp, m->q, m->n, 0.0);
     const dim3 rgrid((unsigned)(qp / 128), (unsigned)(np / ROWRED_CHUNK));
     const int chunks = (int)(np / ROWRED_CHUNK);
@@ -514,7 +553,10 @@ FGP_EXPORT int fgp_predict_cov(fgp_model* m, const fgp_kernel_desc* kernel, cons
     FGP_TRY(check_kernel(m, kernel, &kt));
     begin_timed(m);
     FGP_TRY(stage_queries(m, Xq, ldq, q));
-    FGP_TRY(predict_device(m, kernel, kt, mean_wo_prior != nullptr, 1));
+    m->force_batched_predict = true;  // the covariance needs the transposed solve buffer Bt whatever q is
+    const int rc_pred = predict_device(m, kernel, kt, mean_wo_prior != nullptr, 1);
+    m->force_batched_predict = false;
+    FGP_TRY(rc_pred);
     const int64_t qp = m->qp;
     CU(m, m->kqq.reserve((size_t)qp * qp));
     PairArgs pa = query_pair_args(m);

@@ -75,6 +75,7 @@ struct fgp_model {
     double* pinned = nullptr;              // host staging for results
     size_t pinned_cap = 0;
     bool have_mean = false, have_var = false;
+    bool force_batched_predict = false;    // fgp_predict_cov needs the transposed solve buffer whatever q is
 
     // LML workspace -------------------------------------------------------------------------------------------
     fgp::DevBuf U, Kinv, lml_partial;

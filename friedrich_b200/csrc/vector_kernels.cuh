@@ -139,8 +139,8 @@ __device__ __forceinline__ void wave_fetch_tile(double* dst, const double* src, 
 
 // Forward: L x = b.  x_i = inv_i (b_i - sum_{j<i} L[i,j] x_j)
 static __global__ void __launch_bounds__(TRSV_THREADS)
-trsv_fwd_wave_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ inv, const double* __restrict__ b,
-                     double* x, int* flags) {
+trsv_fwd_wave_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ inv, const double* b, double* x,
+                     int* flags) {  // b may alias x: a block reads its segment of b before it writes that segment of x
     extern __shared__ __align__(128) unsigned char wave_smem[];
     double* inv_s = reinterpret_cast<double*>(wave_smem);
     uint64_t* bar = reinterpret_cast<uint64_t*>(wave_smem + 128 * 128 * 8);
@@ -263,6 +263,30 @@ reduce_kernel(const double* __restrict__ v, const double* __restrict__ w, int64_
         __syncthreads();
     }
     if (threadIdx.x == 0) out[0] = red[0];
+}
+
+// one block per column c of a column-major matrix: out[c] = sum_r M[r + c*ld] * vec[r] (MODE 0) / sum_r M[r + c*ld]^2 (MODE 1);
+// fixed-order tree reduction (deterministic). The single-query latency path of predict.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+col_reduce_kernel(const double* __restrict__ M, int64_t ld, const double* __restrict__ vec, int64_t n, double* out) {
+    __shared__ double red[256];
+    const double* p = M + (int64_t)blockIdx.x * ld;
+    double a0 = 0.0, a1 = 0.0;
+    int64_t i = threadIdx.x;
+    for (; i + 256 < n; i += 512) {
+        const double v0 = p[i], v1 = p[i + 256];
+        if (MODE == 0) { a0 = fma(v0, vec[i], a0); a1 = fma(v1, vec[i + 256], a1); }
+        else { a0 = fma(v0, v0, a0); a1 = fma(v1, v1, a1); }
+    }
+    if (i < n) a0 = (MODE == 0) ? fma(p[i], vec[i], a0) : fma(p[i], p[i], a0);
+    red[threadIdx.x] = a0 + a1;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = red[0];
 }
 
 static __global__ void fill_kernel(double* p, int64_t n, double v) {
