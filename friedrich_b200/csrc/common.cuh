@@ -17,6 +17,14 @@ constexpr int TILE = 128;  // every matrix on the device is padded to a multiple
 
 __host__ __device__ inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
+// Function attributes (opt-in shared memory sizes) are per device: one-time setup is tracked per CUDA device, so that a
+// process holding models on several GPUs configures each of them. Returns the slot of the current device.
+inline bool* per_device_flag(bool (&flags)[64]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return &flags[(dev >= 0 && dev < 64) ? dev : 0];
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Launch context: the stream plus an optional per-kernel-class profiler (CUDA events around each launch on the
 // launching stream; bench.py's roofline figures come from it, include/fgp.h fgp_set_profiling).

@@ -58,7 +58,8 @@ void solve_alpha(fgp_model* m) {
     const int nb = (int)(m->np / TILE);
     int* flags = reinterpret_cast<int*>(m->work.p);  // np doubles of scratch >= 2 nb ints
     cudaMemsetAsync(flags, 0, 2 * (size_t)nb * sizeof(int), m->st);
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};
+    bool& attr_done = *per_device_flag(attr_done_dev);
     if (!attr_done) {  // the block's inverse diagonal tile lives in 128 KiB of dynamic shared memory
         cudaFuncSetAttribute(trsv_fwd_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_WAVE_SMEM);
         cudaFuncSetAttribute(trsv_adj_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_WAVE_SMEM);

@@ -144,7 +144,8 @@ gemm_nt_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ CUten
 }
 
 cudaError_t gemm_nt_prepare() {
-    static bool done = false;
+    static bool done_dev[64] = {};
+    bool& done = *per_device_flag(done_dev);
     if (done) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
     // two CTAs per SM need 2 x 100 KiB of shared memory: ask for the largest carve-out

@@ -284,7 +284,8 @@ potrf_diag_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ inv,
 }
 
 cudaError_t potrf_prepare() {
-    static bool done = false;
+    static bool done_dev[64] = {};
+    bool& done = *per_device_flag(done_dev);
     if (done) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES);
     if (e != cudaSuccess) return e;

@@ -445,3 +445,24 @@ def test_wavefront_solves_beyond_one_resident_wave_n24576():
     assert np.abs(Krows @ alpha - y[idx]).max() < 1e-9
     m = gp.predict(X[idx])                       # posterior mean at training points = (K - s^2 I) alpha
     assert close(m, y[idx] - 0.1 ** 2 * alpha[idx])
+
+
+def test_two_devices_in_one_process():
+    """Per-device one-time kernel setup (opt-in shared memory sizes): a second model on another GPU of the same process
+    must work like the first.  Skipped on single-GPU boxes."""
+    F, N, O, make_dataset, make_inputs = _mods()
+    try:
+        h1 = N.Handle(1)
+    except Exception:
+        pytest.skip("needs a second GPU")
+    h1.close()
+    n, d = 900, 4
+    X, y = make_dataset(0x5EED0010, n, d)
+    Xq = make_inputs(0x5EED0011, 40, d)
+    kern, kd = _kern(F, O, "sqexp", d)
+    g0 = F.GaussianProcess(F.ZeroPrior(), kern, 0.1, None, X, y, device=0)
+    g1 = F.GaussianProcess(F.ZeroPrior(), kern, 0.1, None, X, y, device=1)
+    m0, v0 = g0.predict_mean_variance(Xq)
+    m1, v1 = g1.predict_mean_variance(Xq)
+    assert np.array_equal(np.tril(g0.cholesky_factor()), np.tril(g1.cholesky_factor()))
+    assert np.array_equal(m0, m1) and np.array_equal(v0, v1)
