@@ -936,7 +936,11 @@ FGP_EXPORT double fgp_dbg_exp(double x) { return exp_nonpos(x); }
 
 FGP_EXPORT int fgp_dbg_gemm_occupancy(int device) {
     DeviceGuard dg(device);
-    return gemm_nt_occupancy();
+    return gemm_nt_occupancy(64);
+}
+FGP_EXPORT int fgp_dbg_gemm_occupancy32(int device) {
+    DeviceGuard dg(device);
+    return gemm_nt_occupancy(32);
 }
 
 FGP_EXPORT int fgp_dbg_gemm_bench(int device, int M, int N, int K, int lower, int beta_one, int reps, double* ms_out,

@@ -14,25 +14,48 @@
 
 namespace fgp {
 
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+// Geometry of the two instantiations: CM = rows of the 128x128 tile one CTA computes.
+//   CM = 64  two CTAs per tile, warps 2 x 2 of 32 x 64, 4-stage ring, 2 CTAs per SM: the throughput shape (big launches);
+//   CM = 32  four CTAs per tile, warps 1 x 4 of 32 x 32, 3-stage ring, 3 CTAs per SM: launches of about one wave or less
+//            (panel solves, in-panel and look-ahead updates, the solve steps of predict) — twice as many, half as long
+//            CTAs spread a sub-wave launch evenly over the SMs (a 64-row launch of 150..296 CTAs leaves some SMs with two
+//            CTAs and the rest with one, and lasts as long as the doubly loaded ones).
+// Every output element sums its k-range in the same order in both, so the results are bit-identical.
+template <int CM>
+struct GemmShape {
+    static constexpr int STAGES = (CM == 64) ? GEMM_STAGES : 3;
+    static constexpr int LDA = CM + 4;                              // smem column stride of the A stage (doubles)
+    static constexpr int STAGE_DOUBLES = GEMM_KC * (LDA + GEMM_LDB);
+    static constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8 + 2 * STAGES * 8;
+    static constexpr int SUBS = GEMM_BM / CM;                       // CTAs per 128x128 tile
+    static constexpr int WR = CM / 32;                              // warp grid: WR x WC
+    static constexpr int WC = GEMM_WARPS / WR;
+    static constexpr int NCOL = GEMM_BN / WC;                       // columns per warp
+    static constexpr int NI = NCOL / 8;
+    static constexpr int MIN_CTAS = (CM == 64) ? 2 : 3;
+};
+
+template <int CM>
+__global__ void __launch_bounds__(GEMM_THREADS, GemmShape<CM>::MIN_CTAS)
 gemm_nt_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ CUtensorMap tmA,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC) {
+    using S = GemmShape<CM>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* tiles = reinterpret_cast<double*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)GEMM_STAGES * GEMM_STAGE_DOUBLES * 8);
-    uint64_t* empty = full + GEMM_STAGES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)S::STAGES * S::STAGE_DOUBLES * 8);
+    uint64_t* empty = full + S::STAGES;
 
-    // work item = one 64 x 128 half tile: block pair -> tile (ti, tj), block parity -> row half
+    // work item = CM rows of a 128 x 128 tile: block group -> tile (ti, tj), block index inside the group -> row slice
     int ti, tj;
-    gemm_tile_decode(g, blockIdx.x >> 1, ti, tj);
-    const int half = blockIdx.x & 1;
-    const int m0 = ti * GEMM_BM + half * GEMM_CTA_M, n0 = tj * GEMM_BN;
+    gemm_tile_decode(g, blockIdx.x / S::SUBS, ti, tj);
+    const int sub = blockIdx.x % S::SUBS;
+    const int m0 = ti * GEMM_BM + sub * CM, n0 = tj * GEMM_BN;
     const int kbeg = g.k_from_tile ? GEMM_BM * max(ti, tj) : 0;
     const int nk = (g.K - kbeg) / GEMM_KC;
     const bool diag_tile = g.lower && (ti == tj);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (g.stagger_ns > 0 && (int)blockIdx.x >= g.stagger_lo && (int)blockIdx.x < g.stagger_hi) {
+    if (CM == 64 && g.stagger_ns > 0 && (int)blockIdx.x >= g.stagger_lo && (int)blockIdx.x < g.stagger_hi) {
         uint64_t t0, t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         do {
@@ -41,7 +64,7 @@ gemm_nt_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ CUten
         } while (t1 - t0 < (uint64_t)g.stagger_ns);
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < GEMM_STAGES; ++s) {
+        for (int s = 0; s < S::STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], GEMM_WARPS);
         }
@@ -49,53 +72,53 @@ gemm_nt_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ CUten
     }
     __syncthreads();
 
-    // Operand chunk j -> stage j % STAGES: two TMA tensor copies issued by one lane, a (64+4) x 16 box of A and a (128+4) x 16
-    // box of B. The 4 extra rows are never read: they are the padding that makes the shared-memory column stride 68 / 132.
+    // Operand chunk j -> stage j % STAGES: two TMA tensor copies issued by one lane, a (CM+4) x 16 box of A and a (128+4) x 16
+    // box of B. The 4 extra rows are never read: they are the padding that makes the shared-memory column stride CM+4 / 132.
     auto issue_load = [&](int j) {  // whole warp
         if (FGP_GEMM_EXP & 2) return;
-        const int s = j % GEMM_STAGES;
-        if (j >= GEMM_STAGES) mbar_wait(&empty[s], ((j / GEMM_STAGES) + 1) & 1);  // chunk j - STAGES has left the stage
+        const int s = j % S::STAGES;
+        if (j >= S::STAGES) mbar_wait(&empty[s], ((j / S::STAGES) + 1) & 1);  // chunk j - STAGES has left the stage
         if (lane == 0) {
-            double* dst = tiles + (size_t)s * GEMM_STAGE_DOUBLES;
-            mbar_arrive_expect_tx(&full[s], GEMM_STAGE_DOUBLES * 8);
+            double* dst = tiles + (size_t)s * S::STAGE_DOUBLES;
+            mbar_arrive_expect_tx(&full[s], S::STAGE_DOUBLES * 8);
             tma_load_2d(dst, &tmA, m0, kbeg + j * GEMM_KC, &full[s]);
-            tma_load_2d(dst + GEMM_KC * GEMM_LDA, &tmB, n0, kbeg + j * GEMM_KC, &full[s]);
+            tma_load_2d(dst + GEMM_KC * S::LDA, &tmB, n0, kbeg + j * GEMM_KC, &full[s]);
         }
         __syncwarp();
     };
     if (warp < GEMM_AHEAD && warp < nk) issue_load(warp);
-    // pull the C half tile (128 columns x 512 B) towards L2 now: the epilogue's read-modify-write happens there
-    if (g.beta_one) l2_prefetch(g.C + (int64_t)(n0 + lane + 32 * warp) * g.ldc + m0, GEMM_CTA_M * 8);
+    // pull the C slice (128 columns x CM rows) towards L2 now: the epilogue's read-modify-write happens there
+    if (g.beta_one) l2_prefetch(g.C + (int64_t)(n0 + lane + 32 * warp) * g.ldc + m0, CM * 8);
 
     const int gq = lane >> 2, t = lane & 3;
-    const int wr = warp & 1, wc = warp >> 1;
-    // the top half of a diagonal tile has nothing on or below the diagonal in columns 64..127
-    const bool idle = diag_tile && half == 0 && wc == 1;
-    double acc[4][8][2];
+    const int wr = warp % S::WR, wc = warp / S::WR;
+    // in a diagonal tile a warp whose columns all lie right of the slice's last row has nothing on or below the diagonal
+    const bool idle = diag_tile && (S::NCOL * wc > sub * CM + CM - 1);
+    double acc[4][S::NI][2];
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        for (int ni = 0; ni < S::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
     for (int it = 0; it < nk; ++it) {
         // the warps take turns refilling the ring, GEMM_AHEAD chunks ahead of the one being consumed
         if ((it & (GEMM_WARPS - 1)) == warp && it + GEMM_AHEAD < nk) issue_load(it + GEMM_AHEAD);
-        const int s = it % GEMM_STAGES;
-        if (!(FGP_GEMM_EXP & 2)) mbar_wait(&full[s], (it / GEMM_STAGES) & 1);
+        const int s = it % S::STAGES;
+        if (!(FGP_GEMM_EXP & 2)) mbar_wait(&full[s], (it / S::STAGES) & 1);
         if (!idle) {
-            const double* As = tiles + (size_t)s * GEMM_STAGE_DOUBLES + t * GEMM_LDA + 32 * wr + gq;
-            const double* Bs = tiles + (size_t)s * GEMM_STAGE_DOUBLES + GEMM_KC * GEMM_LDA + t * GEMM_LDB + 64 * wc + gq;
+            const double* As = tiles + (size_t)s * S::STAGE_DOUBLES + t * S::LDA + 32 * wr + gq;
+            const double* Bs = tiles + (size_t)s * S::STAGE_DOUBLES + GEMM_KC * S::LDA + t * GEMM_LDB + S::NCOL * wc + gq;
 #pragma unroll
             for (int kk = 0; kk < GEMM_KC / 4; ++kk) {
-                double fa[4], fb[8];
+                double fa[4], fb[S::NI];
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi) fa[mi] = As[kk * 4 * GEMM_LDA + 8 * mi];
+                for (int mi = 0; mi < 4; ++mi) fa[mi] = As[kk * 4 * S::LDA + 8 * mi];
 #pragma unroll
-                for (int ni = 0; ni < 8; ++ni) fb[ni] = Bs[kk * 4 * GEMM_LDB + 8 * ni];
+                for (int ni = 0; ni < S::NI; ++ni) fb[ni] = Bs[kk * 4 * GEMM_LDB + 8 * ni];
 #pragma unroll
                 for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                    for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], fa[mi], fb[ni]);
+                    for (int ni = 0; ni < S::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], fa[mi], fb[ni]);
             }
         }
         __syncwarp();
@@ -107,29 +130,29 @@ gemm_nt_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ CUten
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 8; ++ni) sum += acc[mi][ni][0] + acc[mi][ni][1];
+            for (int ni = 0; ni < S::NI; ++ni) sum += acc[mi][ni][0] + acc[mi][ni][1];
         if (sum == 12345.678) g.C[0] = sum;
         return;
     }
 
     // ---------------- epilogue ----------------
-    // alpha * acc is staged in the (now idle) operand ring as a dense 64 x 128 column-major image and handed to the TMA
+    // alpha * acc is staged in the (now idle) operand ring as a dense CM x 128 column-major image and handed to the TMA
     // engine in ONE tensor operation: a reduce-add into C (beta = 1: the f64 addition happens at the L2, the SM never reads
     // C) or a plain store (beta = 0). Elements above the diagonal of a diagonal tile are staged as zeros (C + 0 = C).
     __syncthreads();  // every warp has consumed every chunk: no TMA write into the ring is pending, nobody reads it any more
     {
         const double alpha = g.alpha;
         double* stage = tiles + 32 * wr + gq;
-        const int rbase = half * GEMM_CTA_M + 32 * wr + gq;  // row inside the 128x128 tile of this lane's mi = 0 element
+        const int rbase = sub * CM + 32 * wr + gq;  // row inside the 128x128 tile of this lane's mi = 0 element
 #pragma unroll
-        for (int ni = 0; ni < 8; ++ni)
+        for (int ni = 0; ni < S::NI; ++ni)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int cl = 64 * wc + 8 * ni + 2 * t + e;
+                const int cl = S::NCOL * wc + 8 * ni + 2 * t + e;
 #pragma unroll
                 for (int mi = 0; mi < 4; ++mi) {
                     const bool above = diag_tile && (rbase + 8 * mi < cl);
-                    stage[cl * GEMM_CTA_M + 8 * mi] = (idle || above) ? 0.0 : alpha * acc[mi][ni][e];
+                    stage[cl * CM + 8 * mi] = (idle || above) ? 0.0 : alpha * acc[mi][ni][e];
                 }
             }
     }
@@ -143,24 +166,34 @@ gemm_nt_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ CUten
     }
 }
 
+template <int CM>
+static cudaError_t prepare_shape() {
+    cudaError_t e =
+        cudaFuncSetAttribute(gemm_nt_kernel<CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmShape<CM>::SMEM_BYTES);
+    // several CTAs per SM need most of the SM's shared memory: ask for the largest carve-out
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_nt_kernel<CM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return e;
+}
+
 cudaError_t gemm_nt_prepare() {
     static bool done_dev[64] = {};
     bool& done = *per_device_flag(done_dev);
     if (done) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-    // two CTAs per SM need 2 x 100 KiB of shared memory: ask for the largest carve-out
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaError_t e = prepare_shape<64>();
+    if (e == cudaSuccess) e = prepare_shape<32>();
     if (e == cudaSuccess) done = true;
     return e;
 }
 
-int gemm_nt_occupancy() {
+int gemm_nt_occupancy(int cta_rows) {
     int blocks = 0;
     if (gemm_nt_prepare() != cudaSuccess) return -1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, gemm_nt_kernel, GEMM_THREADS, GEMM_SMEM_BYTES) != cudaSuccess)
-        return -1;
-    return blocks;
+    const cudaError_t e =
+        (cta_rows == 32)
+            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, gemm_nt_kernel<32>, GEMM_THREADS, GemmShape<32>::SMEM_BYTES)
+            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, gemm_nt_kernel<64>, GEMM_THREADS, GemmShape<64>::SMEM_BYTES);
+    return e == cudaSuccess ? blocks : -1;
 }
 
 static int g_num_sms = 0;
@@ -267,14 +300,25 @@ int64_t gemm_nt_launch(const GemmArgs& g, const LaunchCtx& ctx) {
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (g_num_sms <= 0) g_num_sms = 148;
     }
-    const int64_t items = 2 * tiles;  // 64 x 128 half tiles
+    // shape: 64-row CTAs for throughput; 32-row CTAs where halving the CTAs lowers the heaviest SM's load (see GemmShape).
+    // With i = 64-row items and S SMs the heaviest SM carries ceil(i / S) units, with 32-row CTAs ceil(2 i / S) / 2: that is
+    // less for i <= S/2 (0.5 vs 1) and for S < i <= 1.5 S (1.5 vs 2); elsewhere the 64-row shape is as balanced and cheaper
+    // (measured: M = 4096, N = 128, K = 384: 45.7 -> 25.2 us; M = 16384, same N, K: 64 us with 64 rows, 74 us with 32).
+#ifdef FGP_GEMM_FORCE_CM
+    const bool small = (FGP_GEMM_FORCE_CM == 32);
+#else
+    const int64_t i64 = 2 * tiles, S = g_num_sms;
+    const bool small = (2 * i64 <= S) || (i64 > S && 2 * i64 <= 3 * S);
+#endif
+    const int cm = small ? 32 : 64;
+    const int64_t items = tiles * (GEMM_BM / cm);
     // one work item per CTA (a persistent variant measured no faster and its never-retiring CTAs starve the look-ahead
     // stream's panel kernels: DESIGN.md "GEMM")
     const unsigned grid = (unsigned)items;
     // de-synchronise the two resident CTAs of every SM (they would otherwise start, and therefore finish, together for the
     // whole launch) by half the lifetime of a CTA pair: 2 x 64x128xK x 2 flop at 128 flop/clk/SM = K x 131 ns, plus overheads
 #ifndef FGP_GEMM_NO_STAGGER
-    if (items >= 8 * (int64_t)g_num_sms) {
+    if (!small && items >= 8 * (int64_t)g_num_sms) {
         p.stagger_lo = g_num_sms;
         p.stagger_hi = 2 * g_num_sms;
         p.stagger_ns = (g.K - (g.k_from_tile ? g.K / 2 : 0)) * 70;
@@ -284,14 +328,15 @@ int64_t gemm_nt_launch(const GemmArgs& g, const LaunchCtx& ctx) {
     // rows of B are addressed by tile COLUMN positions of C, which reach M when the owned columns are strided (sharded).
     alignas(64) CUtensorMap tmA, tmB, tmC;
     const int64_t ncols = g.lower ? g.M : g.N;
-    if (!make_tile_map(&tmA, g.A, g.M, g.K, g.lda, GEMM_LDA, GEMM_KC) || !make_tile_map(&tmB, g.B, ncols, g.K, g.ldb, GEMM_LDB, GEMM_KC) ||
-        !make_tile_map(&tmC, g.C, g.M, ncols, g.ldc, GEMM_CTA_M, GEMM_BN)) {
+    if (!make_tile_map(&tmA, g.A, g.M, g.K, g.lda, cm + 4, GEMM_KC) || !make_tile_map(&tmB, g.B, ncols, g.K, g.ldb, GEMM_LDB, GEMM_KC) ||
+        !make_tile_map(&tmC, g.C, g.M, ncols, g.ldc, cm, GEMM_BN)) {
         if (!g_gemm_error) fprintf(stderr, "libfgp_sm100: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)\n", g.M, g.N, g.K);
         g_gemm_error = true;
         return 0;
     }
     ProfScope ps(ctx, PROF_GEMM, gemm_nt_flops(g));
-    gemm_nt_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, ctx.st>>>(p, tmA, tmB, tmC);
+    if (small) gemm_nt_kernel<32><<<grid, GEMM_THREADS, GemmShape<32>::SMEM_BYTES, ctx.st>>>(p, tmA, tmB, tmC);
+    else gemm_nt_kernel<64><<<grid, GEMM_THREADS, GemmShape<64>::SMEM_BYTES, ctx.st>>>(p, tmA, tmB, tmC);
     return tiles;
 }
 

@@ -23,6 +23,9 @@
 //     one CTA of the SM is in its prologue / epilogue the other keeps the DMMA pipe busy;
 //   * lower-mode launches walk the triangle in bands of GEMM band rows (tile rows), column by column inside a band, so
 //     that the A blocks of a band stay L2-resident while the B blocks stream (gemm_nt_plan / gemm_tile_decode).
+//   * sub-wave launches whose heaviest SM gets lighter that way use a second instantiation with 32-row CTAs (four per tile, 1 x 4
+//     warps of 32 x 32, 3-stage ring, three resident per SM; `GemmShape` in gemm_nt.cu): twice as many, half as long CTAs
+//     spread the latency-bound panel products evenly over the SMs. Both shapes sum every element in the same order.
 //   Splitting the tile by ROWS keeps the in-place products (C aliases A: panel solve, multi-RHS solve) race free: a CTA
 //   only ever reads the rows of A it later overwrites. In lower mode the strict upper triangle of a diagonal tile is left
 //   unchanged by beta = 1 launches and zeroed by beta = 0 launches.
@@ -125,7 +128,7 @@ cudaError_t gemm_nt_prepare();
 bool make_tile_map(CUtensorMap* tm, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols);
 void gemm_nt_flag_error();   // a kernel launch could not be set up (tensor-map encode failure): reported by end_timed
 bool gemm_nt_take_error();  // true once after a launch could not be set up (tensor-map encode failure)
-int gemm_nt_occupancy();  // resident CTAs per SM of the GEMM kernel on the current device (2 by design), -1 on error
+int gemm_nt_occupancy(int cta_rows = 64);  // resident CTAs per SM of the 64-row (2 by design) / 32-row (3) kernel, -1 on error
 // algorithmic flops of one launch (what the roofline figure in bench.py is computed from)
 double gemm_nt_flops(const GemmArgs& g);
 // launches nothing when the problem is empty; returns the number of tiles launched

@@ -173,6 +173,7 @@ double fgp_dbg_exp(double x);
 /* test hook: resident CTAs per SM of the GEMM kernel on `device` (the design point is 2: one CTA's C read-modify-write
  * overlaps the other's DMMA main loop); -1 on error */
 int fgp_dbg_gemm_occupancy(int device);
+int fgp_dbg_gemm_occupancy32(int device); /* the 32-row shape used for sub-wave launches: 3 by design */
 
 /* test hook, host only: the (tile row, tile column) each thread block of a lower-mode GEMM launch computes, for M x N
  * extents and tile-column groups of `grp` columns `stride` apart (the sharded trailing update); returns the tile count. */

@@ -46,7 +46,9 @@ def test_native_library_is_loaded_and_reports_sm100():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape", [(128, 128, 16, 0), (256, 384, 144, 0), (512, 512, 256, 1), (640, 128, 1024, 0)])
+# the last two shapes are large enough for the 64-row CTA shape, the others run the 32-row shape (csrc/gemm_nt.cu)
+@pytest.mark.parametrize("shape", [(128, 128, 16, 0), (256, 384, 144, 0), (512, 512, 256, 1), (640, 128, 1024, 0),
+                                   (2048, 2048, 80, 0), (3072, 3072, 48, 1)])
 def test_gemm_nt_kernel_against_numpy(shape):
     F, N, O, *_ = _mods()
     M, Nn, K, lower = shape
@@ -69,6 +71,7 @@ def test_gemm_nt_kernel_runs_two_ctas_per_sm():
     """Design point of gemm_nt.cu: two 64x128 CTAs resident per SM (one's epilogue overlaps the other's main loop)."""
     F, N, O, *_ = _mods()
     assert N.lib().fgp_dbg_gemm_occupancy(0) == 2
+    assert N.lib().fgp_dbg_gemm_occupancy32(0) == 3   # the 32-row shape of sub-wave launches
 
 
 # ---------------------------------------------------------------------------------------------------------------------
