@@ -115,7 +115,8 @@ int fgp_cholesky_lower(int device, double* A, int64_t lda, int64_t n, int64_t* f
 /* multi-GPU fit (no reference counterpart: the crate is single-threaded) ---------------------------
  * One process per GPU.  The 512-column panels of the covariance matrix are owned block-cyclically; each rank assembles
  * only its own panels (algebra/mod.rs:70-79 restricted to them), the owner of a panel factors it and ncclBroadcast()s it
- * over NVLink, every rank applies it to the panels it owns (one-panel look-ahead).  When the call returns EVERY rank
+ * over NVLink 128 columns at a time while it factors on, every rank applies it to the panels it owns (one-panel
+ * look-ahead).  With one rank the panels are 1024 columns wide from n = 24576 on.  When the call returns EVERY rank
  * holds the complete factor and alpha, so predict / likelihood / lml_gradient run locally (queries shard trivially).
  * fgp_comm_unique_id   rank 0: ncclGetUniqueId into a caller buffer of FGP_COMM_ID_BYTES bytes; the caller ships it to
  *                      the other processes (bench.py: torch.distributed broadcast — plumbing only).
