@@ -99,6 +99,7 @@ SIGNATURES = {
     "fgp_dbg_exp": (C.c_double, [C.c_double]),
     "fgp_dbg_gemm_occupancy": (C.c_int, [C.c_int]),
     "fgp_dbg_gemm_occupancy32": (C.c_int, [C.c_int]),
+    "fgp_dbg_gemm_cta_rows": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "fgp_dbg_gemm_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp]),
     "fgp_dbg_gemm_nt": (C.c_int, [C.c_int, _dp, _i64, _dp, _i64, _dp, _i64, C.c_int, C.c_int, C.c_int, C.c_double,
                                   C.c_int, C.c_int]),

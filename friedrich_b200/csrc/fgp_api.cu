@@ -938,6 +938,11 @@ FGP_EXPORT int fgp_dbg_gemm_occupancy(int device) {
     DeviceGuard dg(device);
     return gemm_nt_occupancy(64);
 }
+FGP_EXPORT int fgp_dbg_gemm_cta_rows(int M, int N, int lower, int num_sms) {
+    GemmArgs g{};
+    g.M = M; g.N = N; g.K = GEMM_KC; g.lower = lower;
+    return gemm_nt_cta_rows(gemm_nt_tiles(g), num_sms);
+}
 FGP_EXPORT int fgp_dbg_gemm_occupancy32(int device) {
     DeviceGuard dg(device);
     return gemm_nt_occupancy(32);

@@ -288,6 +288,11 @@ double gemm_nt_flops(const GemmArgs& g) {
     return 2.0 * GEMM_BM * GEMM_BN * (double)gemm_nt_tiles(g) * g.K;
 }
 
+int gemm_nt_cta_rows(int64_t tiles, int num_sms) {
+    const int64_t i64 = 2 * tiles, S = num_sms;
+    return ((2 * i64 <= S) || (i64 > S && 2 * i64 <= 3 * S)) ? 32 : 64;
+}
+
 int64_t gemm_nt_launch(const GemmArgs& g, const LaunchCtx& ctx) {
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
     const int64_t tiles = gemm_nt_tiles(g);
@@ -307,8 +312,7 @@ int64_t gemm_nt_launch(const GemmArgs& g, const LaunchCtx& ctx) {
 #ifdef FGP_GEMM_FORCE_CM
     const bool small = (FGP_GEMM_FORCE_CM == 32);
 #else
-    const int64_t i64 = 2 * tiles, S = g_num_sms;
-    const bool small = (2 * i64 <= S) || (i64 > S && 2 * i64 <= 3 * S);
+    const bool small = gemm_nt_cta_rows(tiles, g_num_sms) == 32;
 #endif
     const int cm = small ? 32 : 64;
     const int64_t items = tiles * (GEMM_BM / cm);

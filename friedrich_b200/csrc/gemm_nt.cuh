@@ -121,6 +121,7 @@ __host__ __device__ inline void gemm_tile_decode(const GemmArgs& g, int b, int& 
 
 // defined in gemm_nt.cu
 int64_t gemm_nt_tiles(const GemmArgs& g);  // number of 128x128 tiles one launch computes
+int gemm_nt_cta_rows(int64_t tiles, int num_sms);  // 64 or 32: the CTA shape a launch of `tiles` tiles uses (host rule)
 void gemm_nt_plan(GemmArgs& g);             // fills band_rows / n_bands / band_prefix (host)
 cudaError_t gemm_nt_prepare();
 // TMA descriptor of a rows x cols column-major f64 matrix (leading dimension ld) moved in box_rows x box_cols tiles

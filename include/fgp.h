@@ -174,6 +174,9 @@ double fgp_dbg_exp(double x);
 /* test hook: resident CTAs per SM of the GEMM kernel on `device` (the design point is 2: one CTA's C read-modify-write
  * overlaps the other's DMMA main loop); -1 on error */
 int fgp_dbg_gemm_occupancy(int device);
+/* test hook, host only: rows per CTA (64 or 32) the GEMM launch of an M x N (lower != 0: triangular) problem uses on a GPU
+ * with num_sms SMs — 32-row CTAs where they lower the heaviest SM's load (csrc/gemm_nt.cu gemm_nt_cta_rows) */
+int fgp_dbg_gemm_cta_rows(int M, int N, int lower, int num_sms);
 int fgp_dbg_gemm_occupancy32(int device); /* the 32-row shape used for sub-wave launches: 3 by design */
 
 /* test hook, host only: the (tile row, tile column) each thread block of a lower-mode GEMM launch computes, for M x N

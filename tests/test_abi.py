@@ -89,3 +89,22 @@ def test_branch_free_exp_is_accurate_to_two_ulp():
     assert worst <= 2.0, worst
     assert lib.fgp_dbg_exp(-709.0) == 0.0 and lib.fgp_dbg_exp(-float("inf")) == 0.0
     assert math.isnan(lib.fgp_dbg_exp(float("nan")))
+
+
+def test_gemm_cta_shape_rule():
+    """Host rule of csrc/gemm_nt.cu: 32-row CTAs exactly where they lower the heaviest SM's load on a 148-SM part —
+    i = 2 * tiles 64-row items: i <= 74 (0.5 vs 1 unit per SM) or 148 < i <= 222 (1.5 vs 2)."""
+    from friedrich_b200 import _native as N
+    lib = N.lib()
+    rows = lambda M, Nn, lower=0: lib.fgp_dbg_gemm_cta_rows(M, Nn, lower, 148)
+    assert rows(4096, 128) == 32          # panel solve at m = 4096: 32 tiles -> 64 items
+    assert rows(4736, 128) == 32          # 37 tiles -> 74 items: last size of the first window
+    assert rows(4864, 128) == 64          # 38 tiles -> 76 items: one 64-row CTA per SM is as balanced
+    assert rows(9472, 128) == 64          # 74 tiles -> 148 items
+    assert rows(9600, 128) == 32          # 75 tiles -> 150 items: second window (1.5 vs 2 units)
+    assert rows(14208, 128) == 32         # 111 tiles -> 222 items
+    assert rows(14336, 128) == 64         # 112 tiles -> 224 items
+    assert rows(16384, 128) == 64
+    assert rows(1024, 128) == 32 and rows(128, 128) == 32     # the solve steps of predict, single tiles
+    assert rows(16384, 16384, 1) == 64    # trailing updates: the throughput shape
+    assert rows(1024, 1024, 1) == 32      # 36 tiles of a small triangle
