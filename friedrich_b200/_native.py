@@ -77,6 +77,8 @@ SIGNATURES = {
     "fgp_mean_pair_distance": (C.c_int, [_h, _dp]),
     "fgp_download_factor": (C.c_int, [_h, _dp, _i64]),
     "fgp_download_alpha": (C.c_int, [_h, _dp]),
+    "fgp_upload_state": (C.c_int, [_h, _dp, _i64, _i64, _i64, _dp, _dp, _i64]),
+    "fgp_inverse_columns": (C.c_int, [_h, C.POINTER(_i64), _i64, _dp, _i64]),
     "fgp_last_device_ms": (C.c_double, [_h]),
     "fgp_last_launch_count": (_i64, [_h]),
     "fgp_set_profiling": (C.c_int, [_h, C.c_int]),

@@ -56,8 +56,8 @@ PairArgs train_pair_args(const fgp_model* m) {
 void solve_alpha(fgp_model* m) {
     // z = L^-1 y, alpha = L^-T z: one wavefront launch each (csrc/vector_kernels.cuh); flags[0..nb) forward, [nb..2nb) adjoint
     const int nb = (int)(m->np / TILE);
-    int* flags = reinterpret_cast<int*>(m->work.p);  // np doubles of scratch >= 2 nb ints
-    cudaMemsetAsync(flags, 0, 2 * (size_t)nb * sizeof(int), m->st);
+    int* flags = reinterpret_cast<int*>(m->work.p);  // np doubles of scratch >= 2 nb flags + 2 tickets
+    cudaMemsetAsync(flags, 0, (2 * (size_t)nb + 2) * sizeof(int), m->st);
     static bool attr_done_dev[64] = {};
     bool& attr_done = *per_device_flag(attr_done_dev);
     if (!attr_done) {  // the block's inverse diagonal tile lives in 128 KiB of dynamic shared memory
@@ -65,11 +65,15 @@ void solve_alpha(fgp_model* m) {
         cudaFuncSetAttribute(trsv_adj_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_WAVE_SMEM);
         attr_done = true;
     }
-    trsv_fwd_wave_kernel<<<nb, TRSV_THREADS, TRSV_WAVE_SMEM, m->st>>>(m->L.p, m->cap, m->inv.p, m->y.p, m->z.p, flags);
+    trsv_fwd_wave_kernel<<<nb, TRSV_THREADS, TRSV_WAVE_SMEM, m->st>>>(m->L.p, m->cap, m->inv.p, m->y.p, m->z.p, flags,
+                                                                      flags + 2 * nb);
     trsv_adj_wave_kernel<<<nb, TRSV_THREADS, TRSV_WAVE_SMEM, m->st>>>(m->L.p, m->cap, m->invT.p, m->z.p, m->alpha.p, flags + nb,
-                                                                      nb);
+                                                                      flags + 2 * nb + 1, nb);
     m->launches += 2;
 }
+
+// hook for whatever the blocked factorisation caches per panel on top of inv / invT (nothing yet)
+int rebuild_panel_inverses(fgp_model*) { return FGP_OK; }
 
 int reserve_training(fgp_model* m, int64_t cap_rows, int64_t dp, bool keep) {
     // `keep` is used by add_samples when the capacity grows: point arrays and vectors keep their prefix; L is handled by
@@ -124,6 +128,7 @@ int factor_resident(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits&
     }
     m->failed_col = -1;
     m->fitted = true;
+    m->kinv_valid = false;
     return FGP_OK;
 }
 
@@ -202,11 +207,11 @@ int predict_small(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& k
         m->have_mean = true;
     }
     if (want_var) {
-        int* flags = reinterpret_cast<int*>(m->work.p);  // np doubles of scratch >= q * nb ints for q <= 16
-        CU(m, cudaMemsetAsync(flags, 0, (size_t)q * nb * sizeof(int), m->st));
+        int* flags = reinterpret_cast<int*>(m->work.p);  // np doubles of scratch >= q * (nb flags + 1 ticket) for q <= 16
+        CU(m, cudaMemsetAsync(flags, 0, (size_t)q * (nb + 1) * sizeof(int), m->st));
         for (int64_t i = 0; i < q; ++i)
             trsv_fwd_wave_kernel<<<nb, TRSV_THREADS, TRSV_WAVE_SMEM, m->st>>>(m->L.p, m->cap, m->inv.p, Kc + i * np, Kc + i * np,
-                                                                            flags + i * nb);
+                                                                            flags + i * (nb + 1), flags + i * (nb + 1) + nb);
         col_reduce_kernel<1><<<(unsigned)q, 256, 0, m->st>>>(Kc, np, nullptr, np, m->partial.p + qp);
         rowreduce_final_kernel<<<(unsigned)(qp / 128), 128, 0, m->st>>>(m->partial.p + qp, 1, qp, q, 1, dk, m->qnr.p, m->var_d.p);
         m->launches += q + 2;
@@ -663,6 +668,73 @@ FGP_EXPORT int fgp_download_alpha(fgp_model* m, double* alpha) {
     return FGP_OK;
 }
 
+namespace {
+// strict upper triangle of the n_pad x n_pad matrix <- 0 (a serialised nalgebra factor carries NaN there, algebra/mod.rs:67)
+__global__ void zero_strict_upper_kernel(double* A, int64_t ld, int64_t np) {
+    const int64_t c = blockIdx.x;
+    for (int64_t r = threadIdx.x; r < c; r += blockDim.x) A[r + c * ld] = 0.0;
+}
+// out[r + i*ldo] = Kinv[r, cols[i]] from the lower triangle of the symmetric inverse
+__global__ void gather_sym_columns_kernel(const double* __restrict__ Kinv, int64_t ld, int64_t n, const int64_t* __restrict__ cols,
+                                          double* __restrict__ out, int64_t ldo) {
+    const int64_t c = cols[blockIdx.y];
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) out[r + (int64_t)blockIdx.y * ldo] = (r >= c) ? Kinv[r + c * ld] : Kinv[c + r * ld];
+}
+}  // namespace
+
+// Restore a handle from a serialised model (serde round trip of GaussianProcess, mod.rs:58; EMatrix / EVector
+// extendable_matrix.rs:14,62; nalgebra's Cholesky keeps the full n x n matrix with the factor in its lower triangle):
+// training inputs, residual outputs and the factor go back to the device WITHOUT refitting; what the device path caches on
+// top of the reference's state (inverse diagonal blocks, alpha = K^-1 y, z = L^-1 y) is rebuilt from L.
+FGP_EXPORT int fgp_upload_state(fgp_model* m, const double* X, int64_t ldx, int64_t n, int64_t d, const double* y_resid,
+                                const double* L, int64_t ldl) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (!y_resid || !L || ldl < n) return fail(m, FGP_ERR_BAD_ARG, "bad serialised state");
+    begin_timed(m);
+    FGP_TRY(set_inputs(m, X, ldx, n, d));
+    CU(m, cudaMemcpyAsync(m->y.p, y_resid, n * sizeof(double), cudaMemcpyHostToDevice, m->st));
+    const int64_t np = m->np;
+    CU(m, cudaMemset2DAsync(m->L.p, m->cap * sizeof(double), 0, np * sizeof(double), np, m->st));
+    launch_set_identity(m->L.p, m->cap, np, m->st);  // padding block = I (overwritten on the first n diagonal entries)
+    CU(m, cudaMemcpy2DAsync(m->L.p, m->cap * sizeof(double), L, ldl * sizeof(double), n * sizeof(double), n,
+                            cudaMemcpyHostToDevice, m->st));
+    zero_strict_upper_kernel<<<(unsigned)np, 256, 0, m->st>>>(m->L.p, m->cap, np);
+    launch_diag_inverse(m->L.p, m->cap, np / TILE, m->inv.p, m->invT.p, m->st);
+    m->launches += 3;
+    FGP_TRY(rebuild_panel_inverses(m));
+    solve_alpha(m);
+    m->failed_col = -1;
+    m->fitted = true;
+    m->kinv_valid = false;
+    return end_timed(m);
+}
+
+// Selected columns of K^-1 = covmat_cholesky.inverse() (optimizer.rs:32, :169) as left on the device by the last
+// fgp_lml_gradient call (lower triangle stored; symmetrised here).  out is n x ncols column-major.  Tests / diagnostics.
+FGP_EXPORT int fgp_inverse_columns(fgp_model* m, const int64_t* cols, int64_t ncols, double* out, int64_t ldo) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (!m->fitted || !m->kinv_valid) return fail(m, FGP_ERR_NOT_FITTED, "no inverse on the device: call fgp_lml_gradient first");
+    if (!cols || !out || ncols <= 0 || ncols > 4096 || ldo < m->n) return fail(m, FGP_ERR_BAD_ARG, "bad column selection");
+    for (int64_t i = 0; i < ncols; ++i)
+        if (cols[i] < 0 || cols[i] >= m->n) return fail(m, FGP_ERR_BAD_ARG, "column out of range");
+    const int64_t n = m->n;
+    CU(m, m->staging.reserve((size_t)n * ncols + (size_t)ncols));
+    int64_t* dcols = reinterpret_cast<int64_t*>(m->staging.p + (size_t)n * ncols);
+    CU(m, cudaMemcpyAsync(dcols, cols, ncols * sizeof(int64_t), cudaMemcpyHostToDevice, m->st));
+    gather_sym_columns_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)ncols), 256, 0, m->st>>>(m->Kinv.p, m->np, n, dcols,
+                                                                                                 m->staging.p, n);
+    CU(m, cudaMemcpy2DAsync(out, ldo * sizeof(double), m->staging.p, n * sizeof(double), n * sizeof(double), ncols,
+                            cudaMemcpyDeviceToHost, m->st));
+    CU(m, cudaStreamSynchronize(m->st));
+    CU(m, cudaGetLastError());
+    return FGP_OK;
+}
+
 // =================================================================================================================
 // add_samples (mod.rs:173-190 + algebra/mod.rs:97-126)
 FGP_EXPORT int fgp_add_samples(fgp_model* m, const double* Xnew, int64_t ldx, int64_t k, const double* ynew_resid,
@@ -717,12 +789,19 @@ FGP_EXPORT int fgp_add_samples(fgp_model* m, const double* Xnew, int64_t ldx, in
     CU(m, cudaMemcpyAsync(m->info_h, m->info_d, sizeof(int), cudaMemcpyDeviceToHost, m->st));
     solve_alpha(m);
     int rc2 = end_timed(m);
-    if (rc2 != FGP_OK) return rc2;
-    if (*m->info_h != 0) {
-        m->failed_col = *m->info_h - 1;
+    if (rc2 != FGP_OK || *m->info_h != 0) {
+        // The block rows from jb on (old rows of the last partial tile included) have been rebuilt and are now garbage: the
+        // handle goes back to the OLD sample count and needs a full refit (fgp_refit / fgp_fit), which the resident inputs
+        // and outputs of the first n_old samples still allow; the host twin (gp.py) has not appended the new rows either.
+        m->n = n_old;
+        m->np = round_up(n_old, TILE);
         m->fitted = false;
+        if (rc2 != FGP_OK) return rc2;
+        m->failed_col = *m->info_h - 1;
         return fail(m, FGP_ERR_NOT_POSDEF, "Cholesky update failed at column " + std::to_string(m->failed_col));
     }
+    m->failed_col = -1;
+    m->kinv_valid = false;
     return FGP_OK;
 }
 
@@ -868,6 +947,28 @@ int finish_sharded(fgp_model* m, int rc) {
     }
     m->failed_col = -1;
     m->fitted = true;
+    m->kinv_valid = false;
+    return FGP_OK;
+}
+// A rank that fails BEFORE the collective part (argument check, allocation, upload) must not leave the others waiting in
+// ncclBroadcast: every rank reports its local status here and all of them return an error when any one failed.
+int comm_agree(fgp_model* m, int local_rc) {
+    fgp_comm* c = m->comm;
+    if (!c || c->nranks == 1) return local_rc;
+    const NcclApi* nccl = nccl_api();
+    if (!nccl) return local_rc != FGP_OK ? local_rc : fail(m, FGP_ERR_COMM, "libnccl.so.2 could not be loaded");
+    *m->info_h = (local_rc != FGP_OK) ? 1 : 0;
+    const std::string local_msg = m->err;
+    bool ok = cudaMemcpyAsync(m->info_d, m->info_h, sizeof(int), cudaMemcpyHostToDevice, m->st) == cudaSuccess &&
+              nccl->AllReduce(m->info_d, m->info_d, 1, ncclInt, ncclMax, c->comm, m->st) == ncclSuccess &&
+              cudaMemcpyAsync(m->info_h, m->info_d, sizeof(int), cudaMemcpyDeviceToHost, m->st) == cudaSuccess &&
+              cudaStreamSynchronize(m->st) == cudaSuccess;
+    if (local_rc != FGP_OK) {
+        m->err = local_msg;
+        return local_rc;
+    }
+    if (!ok) return fail(m, FGP_ERR_COMM, "status exchange between the ranks failed");
+    if (*m->info_h != 0) return fail(m, FGP_ERR_COMM, "another rank failed before the collective factorisation started");
     return FGP_OK;
 }
 }  // namespace
@@ -881,17 +982,23 @@ FGP_EXPORT int fgp_fit_sharded(fgp_model* m, const double* X, int64_t ldx, int64
     DeviceGuard dg(m->device);
     if (!m->comm) return fail(m, FGP_ERR_COMM, "fgp_comm_init_rank has not been called");
     const bool root = m->comm->rank == 0;
-    if (root && (!X || !y_resid || ldx < n)) return fail(m, FGP_ERR_BAD_ARG, "rank 0 must supply X and y_resid");
-    if (!(noise >= 0.0)) return fail(m, FGP_ERR_BAD_ARG, "The noise parameter should non-negative");
     KernelTraits kt;
-    FGP_TRY(check_kernel(m, kernel, &kt));
     begin_timed(m);
-    FGP_TRY(reserve_inputs(m, n, d));
-    CU(m, cudaMemsetAsync(m->y.p, 0, m->np * sizeof(double), m->st));
-    if (root) {
-        FGP_TRY(upload_colmajor(m, X, ldx, n, d));
-        CU(m, cudaMemcpyAsync(m->y.p, y_resid, n * sizeof(double), cudaMemcpyHostToDevice, m->st));
-    }
+    // rank-local part: anything that can fail here is agreed on before the first collective
+    const auto local = [&]() -> int {
+        if (root && (!X || !y_resid || ldx < n)) return fail(m, FGP_ERR_BAD_ARG, "rank 0 must supply X and y_resid");
+        if (!(noise >= 0.0)) return fail(m, FGP_ERR_BAD_ARG, "The noise parameter should non-negative");
+        FGP_TRY(check_kernel(m, kernel, &kt));
+        FGP_TRY(reserve_inputs(m, n, d));
+        FGP_TRY(reserve_sharded(m));
+        CU(m, cudaMemsetAsync(m->y.p, 0, m->np * sizeof(double), m->st));
+        if (root) {
+            FGP_TRY(upload_colmajor(m, X, ldx, n, d));
+            CU(m, cudaMemcpyAsync(m->y.p, y_resid, n * sizeof(double), cudaMemcpyHostToDevice, m->st));
+        }
+        return FGP_OK;
+    };
+    FGP_TRY(comm_agree(m, local()));
     if (m->comm->nranks > 1) {
         const NcclApi* nccl = nccl_api();
         if (!nccl || nccl->Broadcast(m->staging.p, m->staging.p, (size_t)n * d, ncclDouble, 0, m->comm->comm, m->st) != ncclSuccess ||
@@ -909,11 +1016,15 @@ FGP_EXPORT int fgp_refit_sharded(fgp_model* m, const fgp_kernel_desc* kernel, do
     std::lock_guard<std::mutex> lk(m->mu);
     DeviceGuard dg(m->device);
     if (!m->comm) return fail(m, FGP_ERR_COMM, "fgp_comm_init_rank has not been called");
-    if (m->n <= 0) return fail(m, FGP_ERR_NOT_FITTED, "no resident training set");
-    if (!(noise >= 0.0)) return fail(m, FGP_ERR_BAD_ARG, "The noise parameter should non-negative");
     KernelTraits kt;
-    FGP_TRY(check_kernel(m, kernel, &kt));
     begin_timed(m);
+    const auto local = [&]() -> int {
+        if (m->n <= 0) return fail(m, FGP_ERR_NOT_FITTED, "no resident training set");
+        if (!(noise >= 0.0)) return fail(m, FGP_ERR_BAD_ARG, "The noise parameter should non-negative");
+        FGP_TRY(check_kernel(m, kernel, &kt));
+        return reserve_sharded(m);
+    };
+    FGP_TRY(comm_agree(m, local()));
     int rc = finish_sharded(m, factor_sharded(m, kernel, kt, noise, has_eps, eps));
     int rc2 = end_timed(m);
     return rc != FGP_OK ? rc : rc2;

@@ -9,6 +9,7 @@
 #endif
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <vector>
 
@@ -196,15 +197,30 @@ int gemm_nt_occupancy(int cta_rows) {
     return e == cudaSuccess ? blocks : -1;
 }
 
-static int g_num_sms = 0;
-static bool g_gemm_error = false;
+// Per-device state (a process may hold models on several GPUs and drive them from several threads): the SM count that
+// picks the CTA shape, and the "a launch could not be set up" flag that end_timed() of a model on THAT device consumes.
+static std::atomic<int> g_num_sms[64];
+static std::atomic<bool> g_gemm_error[64];
 
-void gemm_nt_flag_error() { g_gemm_error = true; }
+static int current_device_slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < 64) ? dev : 0;
+}
 
-bool gemm_nt_take_error() {
-    const bool e = g_gemm_error;
-    g_gemm_error = false;
-    return e;
+void gemm_nt_flag_error() { g_gemm_error[current_device_slot()].store(true); }
+
+bool gemm_nt_take_error() { return g_gemm_error[current_device_slot()].exchange(false); }
+
+int gemm_nt_num_sms() {
+    const int slot = current_device_slot();
+    int n = g_num_sms[slot].load(std::memory_order_relaxed);
+    if (n == 0) {
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, slot);
+        if (n <= 0) n = 148;
+        g_num_sms[slot].store(n, std::memory_order_relaxed);
+    }
+    return n;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point lookup (libcuda is not linked)
@@ -299,12 +315,7 @@ int64_t gemm_nt_launch(const GemmArgs& g, const LaunchCtx& ctx) {
     if (tiles <= 0) return 0;
     GemmArgs p = g;
     gemm_nt_plan(p);
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
-    }
+    const int num_sms = gemm_nt_num_sms();
     // shape: 64-row CTAs for throughput; 32-row CTAs where halving the CTAs lowers the heaviest SM's load (see GemmShape).
     // With i = 64-row items and S SMs the heaviest SM carries ceil(i / S) units, with 32-row CTAs ceil(2 i / S) / 2: that is
     // less for i <= S/2 (0.5 vs 1) and for S < i <= 1.5 S (1.5 vs 2); elsewhere the 64-row shape is as balanced and cheaper
@@ -312,7 +323,7 @@ int64_t gemm_nt_launch(const GemmArgs& g, const LaunchCtx& ctx) {
 #ifdef FGP_GEMM_FORCE_CM
     const bool small = (FGP_GEMM_FORCE_CM == 32);
 #else
-    const bool small = gemm_nt_cta_rows(tiles, g_num_sms) == 32;
+    const bool small = gemm_nt_cta_rows(tiles, num_sms) == 32;
 #endif
     const int cm = small ? 32 : 64;
     const int64_t items = tiles * (GEMM_BM / cm);
@@ -322,9 +333,9 @@ int64_t gemm_nt_launch(const GemmArgs& g, const LaunchCtx& ctx) {
     // de-synchronise the two resident CTAs of every SM (they would otherwise start, and therefore finish, together for the
     // whole launch) by half the lifetime of a CTA pair: 2 x 64x128xK x 2 flop at 128 flop/clk/SM = K x 131 ns, plus overheads
 #ifndef FGP_GEMM_NO_STAGGER
-    if (!small && items >= 8 * (int64_t)g_num_sms) {
-        p.stagger_lo = g_num_sms;
-        p.stagger_hi = 2 * g_num_sms;
+    if (!small && items >= 8 * (int64_t)num_sms) {
+        p.stagger_lo = num_sms;
+        p.stagger_hi = 2 * num_sms;
         p.stagger_ns = (g.K - (g.k_from_tile ? g.K / 2 : 0)) * 70;
     }
 #endif
@@ -334,8 +345,8 @@ int64_t gemm_nt_launch(const GemmArgs& g, const LaunchCtx& ctx) {
     const int64_t ncols = g.lower ? g.M : g.N;
     if (!make_tile_map(&tmA, g.A, g.M, g.K, g.lda, cm + 4, GEMM_KC) || !make_tile_map(&tmB, g.B, ncols, g.K, g.ldb, GEMM_LDB, GEMM_KC) ||
         !make_tile_map(&tmC, g.C, g.M, ncols, g.ldc, cm, GEMM_BN)) {
-        if (!g_gemm_error) fprintf(stderr, "libfgp_sm100: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)\n", g.M, g.N, g.K);
-        g_gemm_error = true;
+        if (!g_gemm_error[current_device_slot()].exchange(true))
+            fprintf(stderr, "libfgp_sm100: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)\n", g.M, g.N, g.K);
         return 0;
     }
     ProfScope ps(ctx, PROF_GEMM, gemm_nt_flops(g));

@@ -128,7 +128,8 @@ cudaError_t gemm_nt_prepare();
 // (cuTensorMapEncodeTiled through the runtime's driver entry point; false on failure)
 bool make_tile_map(CUtensorMap* tm, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols);
 void gemm_nt_flag_error();   // a kernel launch could not be set up (tensor-map encode failure): reported by end_timed
-bool gemm_nt_take_error();  // true once after a launch could not be set up (tensor-map encode failure)
+bool gemm_nt_take_error();  // true once after a launch on the CURRENT device could not be set up (tensor-map encode failure)
+int gemm_nt_num_sms();      // SM count of the current device (cached per device)
 int gemm_nt_occupancy(int cta_rows = 64);  // resident CTAs per SM of the 64-row (2 by design) / 32-row (3) kernel, -1 on error
 // algorithmic flops of one launch (what the roofline figure in bench.py is computed from)
 double gemm_nt_flops(const GemmArgs& g);

@@ -158,6 +158,7 @@ int lml_gradient_device(fgp_model* m, const fgp_kernel_desc* kd, const KernelTra
     }
     if (!scaled) grads[P] = noise * (h[50] - h[2 * pmax]);      // optimizer.rs:54-57
     if (scale_out) *scale_out = scale;
+    m->kinv_valid = true;
     return FGP_OK;
 }
 

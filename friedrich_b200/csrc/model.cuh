@@ -79,6 +79,7 @@ struct fgp_model {
 
     // LML workspace -------------------------------------------------------------------------------------------
     fgp::DevBuf U, Kinv, lml_partial;
+    bool kinv_valid = false;               // Kinv holds K^-1 of the CURRENT factor (set by fgp_lml_gradient, cleared by every refit)
 
     // multi-GPU -----------------------------------------------------------------------------------------------
     fgp_comm* comm = nullptr;

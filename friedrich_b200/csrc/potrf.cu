@@ -283,6 +283,44 @@ potrf_diag_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ inv,
     DIAG_MARK(19);
 }
 
+// X = L_jj^-1 of every 128 x 128 diagonal tile of an already factored matrix (fgp_upload_state: a deserialised factor has no
+// inverse blocks yet).  One CTA per tile, thread c owns column c of X: forward substitution on e_c with the tile's rows
+// broadcast from shared memory.  One-off O(n 128^2) work, not on any hot path.
+__global__ void __launch_bounds__(128) diag_inverse_kernel(const double* __restrict__ L, int64_t ld, double* __restrict__ inv,
+                                                          double* __restrict__ invT) {
+    extern __shared__ __align__(16) double Ls[];  // [128][DIAG_DS] row-major, lower triangle
+    const int c = threadIdx.x;
+    const double* A = L + (int64_t)blockIdx.x * TILE * (ld + 1);
+    for (int idx = c; idx < 128 * 128; idx += 128) {
+        const int r = idx & 127, cc = idx >> 7;
+        Ls[r * DIAG_DS + cc] = (r >= cc) ? A[r + (int64_t)cc * ld] : 0.0;
+    }
+    __syncthreads();
+    double x[128];
+    for (int r = 0; r < 128; ++r) {
+        double acc = (r == c) ? 1.0 : 0.0;
+        const double* lr = Ls + r * DIAG_DS;
+        for (int k = 0; k < r; ++k) acc = fma(-lr[k], (k >= c) ? x[k] : 0.0, acc);
+        x[r] = (r >= c) ? acc / lr[r] : 0.0;
+    }
+    double* X = inv + (int64_t)blockIdx.x * TILE * TILE;
+    double* XT = invT + (int64_t)blockIdx.x * TILE * TILE;
+    for (int r = 0; r < 128; ++r) {
+        X[r + c * 128] = x[r];
+        XT[c + r * 128] = x[r];
+    }
+}
+
+void launch_diag_inverse(const double* L, int64_t ld, int64_t nb, double* inv, double* invT, cudaStream_t st) {
+    static bool done_dev[64] = {};
+    bool& done = *per_device_flag(done_dev);
+    if (!done) {
+        cudaFuncSetAttribute(diag_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * DIAG_DS * 8);
+        done = true;
+    }
+    diag_inverse_kernel<<<(unsigned)nb, 128, 128 * DIAG_DS * 8, st>>>(L, ld, inv, invT);
+}
+
 cudaError_t potrf_prepare() {
     static bool done_dev[64] = {};
     bool& done = *per_device_flag(done_dev);

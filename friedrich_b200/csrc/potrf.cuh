@@ -41,6 +41,8 @@ struct PotrfCounters {
 
 // defined in potrf.cu
 cudaError_t potrf_prepare();
+// inv / invT of the nb diagonal tiles of an already factored matrix (restoring a serialised model, fgp_upload_state)
+void launch_diag_inverse(const double* L, int64_t ld, int64_t nb, double* inv, double* invT, cudaStream_t st);
 // Factor block columns [jb_begin, np/128) of the np x np matrix A (ld = lda) in place. Block columns before
 // jb_begin must already hold final factor values in ALL rows (used by add_samples: the caller has applied them to
 // the trailing block). invdiag / invdiagT: [np/128][128*128] (inverse blocks and their transposes). info: device int, 0 on entry.

@@ -51,15 +51,21 @@ static void update_from_buffer(fgp_model* m, const double* buf, int64_t J, int64
     cnt->launches += gemm_nt_launch(g, c) > 0;
 }
 
+int reserve_sharded(fgp_model* m) {
+    fgp_comm* cm = m->comm;
+    const int64_t W = (int64_t)panel_tiles(m->np, cm->nranks) * TILE;
+    CU(m, cm->pbuf[0].reserve((size_t)m->np * W));
+    CU(m, cm->pbuf[1].reserve((size_t)m->np * W));
+    return FGP_OK;
+}
+
 int factor_sharded(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& kt, double noise, int has_eps, double eps) {
     fgp_comm* cm = m->comm;
     const int P = cm->nranks, r = cm->rank;
     const NcclApi* nccl = nccl_api();
     if (P > 1 && !nccl) return fail(m, FGP_ERR_COMM, "libnccl.so.2 could not be loaded");
     const int64_t np = m->np, nb = np / TILE, PANEL_TILES = panel_tiles(np, P), NP = (nb + PANEL_TILES - 1) / PANEL_TILES;
-    const int64_t W = (int64_t)PANEL_TILES * TILE;
-    CU(m, cm->pbuf[0].reserve((size_t)np * W));
-    CU(m, cm->pbuf[1].reserve((size_t)np * W));
+    FGP_TRY(reserve_sharded(m));  // no-op when the entry point has already done it (before the status exchange)
     CU(m, cudaMemsetAsync(m->info_d, 0, sizeof(int), m->st));
     cm->bcast_bytes = 0.0;
 

@@ -25,6 +25,9 @@ namespace fgp {
 // panel p (PANEL_TILES block columns) is owned by rank p % nranks
 inline int shard_owner(int64_t panel, int nranks) { return (int)(panel % nranks); }
 
+// panel buffers for the current problem size (rank-local allocation; entry points call it BEFORE the cross-rank status exchange)
+int reserve_sharded(fgp_model* m);
+
 // Gram assembly of the owned panels + the sharded factorisation; on return every rank holds the complete factor in m->L.
 int factor_sharded(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& kt, double noise, int has_eps, double eps);
 

@@ -105,8 +105,9 @@ __device__ __forceinline__ double tile_apply_smem_512(const double* Ms, const do
 // ---- wavefront triangular solves: ONE launch per solve instead of one per block column -------------------------------
 // Block i of the grid owns the 128 unknowns of block row i. It consumes the solution blocks it depends on as their owners
 // publish them (a flag per block in global memory, release/acquire), so the 128-step dependency chain costs a flag
-// round trip per step instead of a kernel launch.  Blocks only ever wait for LOWER block indices, which the hardware
-// dispatches first, so the wait cannot deadlock however many blocks are resident.  Everything that does not depend on
+// round trip per step instead of a kernel launch.  A CTA takes its block index from an atomic TICKET at kernel start, not
+// from blockIdx: a block only ever waits for lower tickets, i.e. for CTAs that are already running, so the wait cannot
+// deadlock however many blocks are resident and in whatever order the hardware dispatches them.  Everything that does not depend on
 // the awaited block is fetched BEFORE the wait: the block's inverse diagonal tile arrives in shared memory by TMA bulk
 // copies at kernel start, and the L tile of each step is loaded into registers ahead of its flag.  The arithmetic (order
 // of the block updates j = 0, 1, ... and the mat-vec reductions) does not depend on the timing: results are deterministic.
@@ -140,14 +141,17 @@ __device__ __forceinline__ void wave_fetch_tile(double* dst, const double* src, 
 // Forward: L x = b.  x_i = inv_i (b_i - sum_{j<i} L[i,j] x_j)
 static __global__ void __launch_bounds__(TRSV_THREADS)
 trsv_fwd_wave_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ inv, const double* b, double* x,
-                     int* flags) {  // b may alias x: a block reads its segment of b before it writes that segment of x
+                     int* flags, int* ticket) {  // b may alias x: a block reads its segment of b before it writes that segment of x
     extern __shared__ __align__(128) unsigned char wave_smem[];
     double* inv_s = reinterpret_cast<double*>(wave_smem);
     uint64_t* bar = reinterpret_cast<uint64_t*>(wave_smem + 128 * 128 * 8);
     __shared__ double xs[128];
     __shared__ double red[512];
+    __shared__ int s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1);
+    __syncthreads();
     const int r = threadIdx.x & 127;
-    const int i = blockIdx.x;
+    const int i = s_ticket;
     const int64_t row0 = (int64_t)i * 128;
     wave_fetch_tile(inv_s, inv + (int64_t)i * 128 * 128, bar);
     double v = 0.0;
@@ -168,20 +172,23 @@ trsv_fwd_wave_kernel(const double* __restrict__ L, int64_t ld, const double* __r
     wave_publish(flags + i);
 }
 
-// Adjoint: L^T x = b, from the last block.  Grid block g owns block column i = nb-1-g:
+// Adjoint: L^T x = b, from the last block.  The CTA with ticket g owns block column i = nb-1-g:
 // x_i = inv_i^T (b_i - sum_{j>i} L[j,i]^T x_j); warp w owns columns 8w .. 8w+7 of a tile, a lane reads rows lane, lane+32,
 // lane+64, lane+96 of each (32 independent loads), then eight shuffle reductions.
 static __global__ void __launch_bounds__(TRSV_THREADS)
 trsv_adj_wave_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ invT, const double* __restrict__ b,
-                     double* x, int* flags, int nb) {
+                     double* x, int* flags, int* ticket, int nb) {
     extern __shared__ __align__(128) unsigned char wave_smem[];
     double* inv_s = reinterpret_cast<double*>(wave_smem);
     uint64_t* bar = reinterpret_cast<uint64_t*>(wave_smem + 128 * 128 * 8);
     __shared__ double xs[128];
     __shared__ double bs[128];
     __shared__ double red[512];
+    __shared__ int s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1);
+    __syncthreads();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int i = nb - 1 - (int)blockIdx.x;
+    const int i = nb - 1 - s_ticket;
     wave_fetch_tile(inv_s, invT + (int64_t)i * 128 * 128, bar);
     if (tid < 128) bs[tid] = b[(int64_t)i * 128 + tid];
     for (int j = nb - 1; j > i; --j) {

@@ -222,6 +222,41 @@ class GaussianProcess:
         self._h.check(N.lib().fgp_download_factor(self._h.ptr, N.dptr(L), n))
         return L
 
+    # -- serde (feature friedrich_serde: mod.rs:58, extendable_matrix.rs:14,62, kernel.rs:506, prior.rs:42) ------------
+    def to_state(self):
+        """What `#[derive(Serialize)]` writes for a GaussianProcess: prior, kernel, noise, cholesky_epsilon, training inputs
+        and (residual) outputs, and covmat_cholesky as nalgebra keeps it (n x n, factor in the lower triangle, NaN above).
+        Plain Python / numpy objects: pickle, json or npz them as you like."""
+        return dict(prior=self.prior, kernel=self.kernel, noise=self.noise, cholesky_epsilon=self.cholesky_epsilon,
+                    training_inputs=self._X_host.copy(order="F"), training_outputs=self._y_host.copy(),
+                    covmat_cholesky=self.cholesky_factor())
+
+    @classmethod
+    def from_state(cls, state, device=0):
+        """`Deserialize`: the model goes back to the GPU without refitting (fgp_upload_state rebuilds only what the device
+        path caches on top of the reference's state)."""
+        self = cls.__new__(cls)
+        self.prior, self.kernel = state["prior"], state["kernel"]
+        self.noise, self.cholesky_epsilon = float(state["noise"]), state["cholesky_epsilon"]
+        X = N.fcol(state["training_inputs"])
+        y = np.ascontiguousarray(state["training_outputs"], dtype=np.float64)
+        L = N.fcol(state["covmat_cholesky"])
+        assert X.shape[0] == y.shape[0] == L.shape[0] == L.shape[1]
+        self._h = N.Handle(device)
+        self._d = X.shape[1]
+        self._X_host, self._y_host = X, y
+        self._h.check(N.lib().fgp_upload_state(self._h.ptr, N.dptr(X), X.shape[0], X.shape[0], X.shape[1], N.dptr(y),
+                                               N.dptr(L), L.shape[0]))
+        return self
+
+    def inverse_columns(self, cols):
+        """Columns of K^-1 left on the device by the last (scaled_)gradient_marginal_likelihood call (diagnostics)."""
+        cols = np.ascontiguousarray(cols, dtype=np.int64)
+        out = np.zeros((self.n_samples, len(cols)), order="F")
+        self._h.check(N.lib().fgp_inverse_columns(self._h.ptr, cols.ctypes.data_as(C.POINTER(C.c_int64)), len(cols),
+                                                  N.dptr(out), out.shape[0]))
+        return out
+
     # -- mod.rs:173-190 -------------------------------------------------------------------------------------------------
     def add_samples(self, inputs, outputs):
         X, _ = _as_matrix(inputs)

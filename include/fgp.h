@@ -57,7 +57,10 @@ const char* fgp_version(void);
  * fgp_set_outputs    EVector::assign after a prior refit (mod.rs:420, extendable_matrix.rs:107-111).
  * fgp_add_samples    EMatrix/EVector::add_rows + add_rows_cholesky_cov_matrix (mod.rs:181-189, algebra/mod.rs:97-126):
  *                    k sequential insert_column(end) == block update of the factor; no failure check in the
- *                    reference (sqrt of a negative gives NaN) — here a non-positive pivot returns FGP_ERR_NOT_POSDEF.
+ *                    reference (sqrt of a negative gives NaN) — here a non-positive pivot returns FGP_ERR_NOT_POSDEF,
+ *                    or takes the substitute when has_eps is set (the reference's insert_column never consults
+ *                    cholesky_epsilon; with has_eps = 0 the behaviour differs only where the reference produces NaN).
+ *                    On failure the handle keeps the OLD sample count and must be refitted (fgp_refit) before use.
  */
 int fgp_set_inputs(fgp_model* m, const double* X, int64_t ldx, int64_t n, int64_t d);
 int fgp_fit(fgp_model* m, const double* X, int64_t ldx, int64_t n, int64_t d, const double* y_resid,
@@ -106,6 +109,16 @@ int fgp_mean_pair_distance(fgp_model* m, double* out);
  */
 int fgp_download_factor(fgp_model* m, double* L, int64_t ldl);
 int fgp_download_alpha(fgp_model* m, double* alpha);
+/* fgp_upload_state     the inverse of the two downloads — deserialising a saved GaussianProcess (serde feature: mod.rs:58,
+ *                      EMatrix / EVector extendable_matrix.rs:14,62; nalgebra's Cholesky stores the n x n matrix whose lower
+ *                      triangle is the factor): X (n x d, ld = ldx), y_resid and L (n x n, ld = ldl; the strict upper triangle
+ *                      is ignored, NaN allowed) become resident WITHOUT refitting; the inverse diagonal blocks, alpha and
+ *                      L^-1 y that the device path caches are rebuilt from L.  The handle then behaves as after fgp_fit.
+ * fgp_inverse_columns  selected columns of K^-1 (`covmat_cholesky.inverse()`, optimizer.rs:32, :169) as left on the device
+ *                      by the last fgp_lml_gradient call; out is n x ncols, ld = ldo.  Diagnostics / tests. */
+int fgp_upload_state(fgp_model* m, const double* X, int64_t ldx, int64_t n, int64_t d, const double* y_resid,
+                     const double* L, int64_t ldl);
+int fgp_inverse_columns(fgp_model* m, const int64_t* cols, int64_t ncols, double* out, int64_t ldo);
 
 /* Cholesky of a caller-supplied SPD matrix with the same device factorisation: MultivariateNormal::new
  * (src/gaussian_process/multivariate_normal.rs:54-59, `covariance.cholesky().expect(..).unpack()`). A is n x n

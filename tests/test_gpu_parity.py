@@ -469,3 +469,159 @@ def test_two_devices_in_one_process():
     m1, v1 = g1.predict_mean_variance(Xq)
     assert np.array_equal(np.tril(g0.cholesky_factor()), np.tril(g1.cholesky_factor()))
     assert np.array_equal(m0, m1) and np.array_equal(v0, v1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2] and configs[4] at (or near) config size, and the state round trip
+def test_config5_add_samples_16384_plus_1024():
+    """configs[4]: fit n=16384 d=16, add_samples k=1024 (algebra/mod.rs:97-126).  The oracle's sequential append would take
+    hours, so the check is the size-independent identity the block update must satisfy: the updated factor equals the
+    from-scratch device factor of all 17408 rows (new block rows to 1e-10 Frobenius, old block bit-identical because it is
+    not touched), and both models predict the same.  Also exercises the capacity regrowth copy of the 2.1 GB factor."""
+    F, N, O, make_dataset, make_inputs = _mods()
+    n0, k, d = 16384, 1024, 16
+    X, y = make_dataset(0x5EED0005, n0 + k, d)
+    kern, kd = _kern(F, O, "sqexp", d)
+    gp = F.GaussianProcess(F.ZeroPrior(), kern, 0.1, None, X[:n0], y[:n0])
+    L0 = np.tril(gp.cholesky_factor())
+    gp.add_samples(X[n0:], y[n0:])
+    assert gp.n_samples == n0 + k
+    L = np.tril(gp.cholesky_factor())
+    assert np.array_equal(L[:n0, :n0], L0)                     # insert_column(end) never changes the old factor
+    del L0
+    scratch = F.GaussianProcess(F.ZeroPrior(), kern, 0.1, None, X, y)
+    Ls = np.tril(scratch.cholesky_factor())
+    assert frob_rel(L[n0:], Ls[n0:]) < L_RTOL                  # the 1024 new block rows
+    assert frob_rel(L[:n0, :n0], Ls[:n0, :n0]) < L_RTOL
+    # rows of K on the host (oracle kernel function) against L L^T on probe rows among the NEW samples
+    idx = n0 + np.random.default_rng(5).choice(k, 16, replace=False)
+    Krows = O.make_covariance_matrix(kd, X[idx], X)
+    Krows[np.arange(16), idx] += 0.1 ** 2
+    assert np.abs(L[idx] @ L.T - Krows).max() < 1e-12 * (n0 + k)
+    del L, Ls
+    Xq = make_inputs(0x5EED0006, 256, d)
+    m1, v1 = gp.predict_mean_variance(Xq)
+    m2, v2 = scratch.predict_mean_variance(Xq)
+    assert close(m1, m2) and close(v1, v2)
+
+
+def test_config3_matern_scaled_adam_against_oracle_n2048():
+    """configs[2] at a size the oracle still finishes (n=2048, d=16, Matern-5/2): three iterations of the scaled ADAM loop
+    (optimizer.rs:211-283) — scale, gradients, parameters, noise per iteration.  n=2048 = 16 tile rows runs the K^-1 = U U^T
+    GEMM in its 64-row / multi-wave form and the shrinking-row TRSM over 16 block columns (n=400 elsewhere is 4 tiles)."""
+    F, N, O, make_dataset, make_inputs = _mods()
+    n, d = 2048, 16
+    X, y = make_dataset(0x5EED0003, n, d)
+    ls = math.sqrt(d / 6.0)
+    gp = F.GaussianProcess(F.ZeroPrior(), F.Matern2(ls, 1.0), 0.1, None, X, y)
+    gp.fit_parameters(False, True, 3, 0.0)
+    ref = O.OracleGaussianProcess(O.ZeroPrior(), O.KernelDesc.make([O.K_MATERN2], [ls, 1.0]), 0.1, None, X, y)
+    ref.fit_parameters(False, True, 3, 0.0)
+    assert len(gp.trace) == len(ref.trace) == 3
+    for a, b in zip(gp.trace, ref.trace):
+        assert abs(a["scale"] - b["scale"]) < 1e-8 * abs(b["scale"])
+        assert np.allclose(a["grads"], b["grads"], rtol=1e-7, atol=1e-8)
+        assert np.allclose(a["params"], b["params"], rtol=1e-8)
+        assert abs(a["noise"] - b["noise"]) < 1e-8 * b["noise"]
+    assert frob_rel(np.tril(gp.cholesky_factor()), np.tril(ref.L)) < L_RTOL
+
+
+def test_config3_inverse_identity_n16384():
+    """configs[2] at full size (Matern-5/2, n=16384, d=16): the explicit inverse behind the LML gradient
+    (`covmat_cholesky.inverse()`, optimizer.rs:169 -> U = L^-T by the shrinking-row TRSM, K^-1 = U U^T by the k_from_tile
+    GEMM) checked by identities the oracle cannot afford here: K[probe rows] K^-1[:, probe cols] = I, K^-1[:, cols]^T y =
+    alpha[cols] (alpha comes from the independent wavefront solves), and the scaled gradient's scale = y.alpha / n."""
+    F, N, O, make_dataset, make_inputs = _mods()
+    n, d = 16384, 16
+    X, y = make_dataset(0x5EED0003, n, d)
+    ls = math.sqrt(d / 6.0)
+    kd = O.KernelDesc.make([O.K_MATERN2], [ls, 1.0])
+    gp = F.GaussianProcess(F.ZeroPrior(), F.Matern2(ls, 1.0), 0.1, None, X, y)
+    scale, grads = gp.scaled_gradient_marginal_likelihood()
+    assert np.all(np.isfinite(grads))
+    rng = np.random.default_rng(16384)
+    cols = np.sort(rng.choice(n, 32, replace=False))
+    cols[0], cols[-1] = 0, n - 1                               # first and last block column included
+    Kinv = gp.inverse_columns(cols)
+    Krows = O.make_covariance_matrix(kd, X[cols], X)
+    Krows[np.arange(32), cols] += 0.1 ** 2
+    assert np.abs(Krows @ Kinv - np.eye(32)).max() < 1e-9
+    alpha = np.zeros(n)
+    gp._h.check(N.lib().fgp_download_alpha(gp._h.ptr, N.dptr(alpha)))
+    assert np.allclose(Kinv.T @ y, alpha[cols], rtol=1e-8, atol=1e-10)
+    assert abs(scale - float(y @ alpha) / n) < 1e-10 * abs(scale)
+    # the gradient's trace term against the same columns: tr(K^-1 G_p) restricted to the probe columns is not available
+    # without G_p, but K^-1's diagonal must be positive and below 1/noise^2
+    dg = Kinv[cols, np.arange(32)]
+    assert np.all(dg > 0) and np.all(dg < 1.0 / 0.1 ** 2 + 1e-9)
+
+
+def test_state_round_trip_restores_model_without_refit():
+    """serde round trip (mod.rs:58): download -> destroy -> upload -> identical predictions, factor and likelihood."""
+    import pickle
+    F, N, O, make_dataset, make_inputs = _mods()
+    n, d = 1000, 5
+    X, y = make_dataset(0x5EED0020, n, d)
+    Xq = make_inputs(0x5EED0021, 300, d)
+    kern, kd = _kern(F, O, "matern2", d)
+    gp = F.GaussianProcess(F.ConstantPrior(0.3), kern, 0.1, None, X, y)
+    m0, v0 = gp.predict_mean_variance(Xq)
+    m1 = gp.predict(Xq[:3])                                    # latency path (q <= 16)
+    lik0, L0 = gp.likelihood(), gp.cholesky_factor()
+    blob = pickle.dumps(gp.to_state())
+    gp._h.close()
+    del gp
+    gp2 = F.GaussianProcess.from_state(pickle.loads(blob))
+    assert np.array_equal(np.tril(gp2.cholesky_factor()), np.tril(L0))
+    m, v = gp2.predict_mean_variance(Xq)
+    assert np.allclose(m, m0, rtol=1e-12, atol=1e-13) and np.allclose(v, v0, rtol=1e-11, atol=1e-13)
+    assert np.allclose(gp2.predict(Xq[:3]), m1, rtol=1e-12, atol=1e-13)
+    assert abs(gp2.likelihood() - lik0) < 1e-10 * abs(lik0)
+    # the restored model keeps working as a model: add_samples and the optimiser's gradient
+    Xn, yn = make_dataset(0x5EED0022, 130, d)
+    gp2.add_samples(Xn, yn)
+    ref = O.OracleGaussianProcess(O.ConstantPrior(0.3), kd, 0.1, None, X, y)
+    ref.add_samples(Xn, yn)
+    assert frob_rel(np.tril(gp2.cholesky_factor()), np.tril(ref.L)) < L_RTOL
+    s, g = gp2.scaled_gradient_marginal_likelihood()
+    sr, gr = ref.gradient_marginal_likelihood(scaled=True)
+    assert abs(s - sr) < 1e-9 * abs(sr) and np.allclose(g, gr, rtol=1e-8, atol=1e-9)
+
+
+def test_failing_column_is_exact_when_the_defect_is_structural():
+    """nalgebra reports the FIRST column whose pivot is not positive.  With a leading block that is safely positive definite
+    and one diagonal entry pushed far negative the failing column is unambiguous for any summation order: the device
+    factorisation must report exactly that column (MultivariateNormal::new path, multivariate_normal.rs:54-59)."""
+    F, N, O, make_dataset, make_inputs = _mods()
+    n = 640
+    rng = np.random.default_rng(12)
+    M = rng.standard_normal((n, n + 8))
+    A0 = np.asfortranarray(M @ M.T / n + 0.5 * np.eye(n))
+    for j0 in (0, 37, 128, 300, 639):
+        A = A0.copy(order="F")
+        A[j0, j0] = -3.0
+        ref = A.copy(order="F")
+        assert O.cholesky_inplace(ref) == j0 + 1
+        failed = C.c_int64(-7)
+        rc = N.lib().fgp_cholesky_lower(0, N.dptr(A), n, n, C.byref(failed))
+        assert rc == N.FGP_ERR_NOT_POSDEF and failed.value == j0, (j0, failed.value)
+    A = A0.copy(order="F")
+    failed = C.c_int64(-7)
+    assert N.lib().fgp_cholesky_lower(0, N.dptr(A), n, n, C.byref(failed)) == 0 and failed.value == -1
+    ref = A0.copy(order="F")
+    assert O.cholesky_inplace(ref) == 0
+    assert frob_rel(np.tril(A), np.tril(ref)) < L_RTOL and np.all(A[np.triu_indices(n, 1)] == 0.0)
+
+
+def test_add_samples_failure_leaves_a_refittable_handle():
+    """a failed block update must not leave the handle with the new sample count."""
+    F, N, O, make_dataset, make_inputs = _mods()
+    n0, d = 200, 3
+    X, y = make_dataset(91, n0, d)
+    gp = F.GaussianProcess(F.ZeroPrior(), F.Exponential(0.9, 1.0), 0.0, None, X, y)   # noise 0: duplicates are singular
+    m0 = gp.predict(X[:5])
+    with pytest.raises(ArithmeticError):
+        gp.add_samples(np.vstack([X[:40], X[:40]]), np.concatenate([y[:40], y[:40]]))
+    assert gp.n_samples == n0
+    gp._refit()
+    assert np.allclose(gp.predict(X[:5]), m0, rtol=1e-9, atol=1e-11)
