@@ -41,9 +41,27 @@ WORKLOADS = {
 }
 
 
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per gemm_nt launch, averaged over the launches of one fit,
-# from the ncu capture named in DESIGN.md "Measurement" (profiles/); None until a capture exists for the workload.
-GEMM_TRAFFIC_BYTES_PER_LAUNCH = {"metric": 88.73e6}  # profiles/gemm_dram_fit16k_r01h.csv: 27.95 GB over the 315 launches of one fit
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per gemm_nt launch, averaged over the launches of one fit: read
+# from the committed ncu capture of the SHIPPED build (tools/ncu_summary.py writes the CSV; profiles/ is the judged copy).
+GEMM_TRAFFIC_CSV = {"metric": "profiles/gemm_dram_fit16k_r02.csv"}
+
+
+def gemm_traffic_bytes_per_launch(workload):
+    """(bytes per launch, launches, file) from the ncu CSV rows `kernel,dram_bytes_read,dram_bytes_write` of gemm_nt_kernel, or
+    (None, 0, file) when no capture of this build is committed."""
+    rel = GEMM_TRAFFIC_CSV.get(workload)
+    path = os.path.join(ROOT, rel) if rel else None
+    if not path or not os.path.exists(path):
+        return None, 0, rel
+    import csv
+    total, launches = 0.0, 0
+    with open(path, newline="") as f:
+        for row in csv.DictReader(l for l in f if not l.startswith("#")):
+            if "gemm_nt_kernel" not in row.get("kernel", ""):
+                continue
+            total += float(row["dram_bytes_read"]) + float(row["dram_bytes_write"])
+            launches += 1
+    return (total / launches if launches else None), launches, rel
 
 
 def fit_flops(n, d):
@@ -139,23 +157,47 @@ def time_oracle(n, d, q, steps, warmup):
     return dt, flops
 
 
+def cpu_port_scaling(d, sizes=(1024, 2048, 4096)):
+    """Oracle fit at a few sizes: seconds, flop rate, and the exponent of t ~ n^p fitted over them (SURVEY §8d asks for the
+    n^3 extrapolation to be shown, not assumed)."""
+    from friedrich_b200.synthetic import make_dataset
+    from oracle import oracle as O
+    rows = []
+    for ns in sizes:
+        X, y = make_dataset(0x5EED0001, ns, d)
+        kdesc = O.KernelDesc.make([O.K_SQUARED_EXP], [math.sqrt(d / 6.0), 1.0])
+        t0 = time.perf_counter()
+        O.OracleGaussianProcess(O.ZeroPrior(), kdesc, 0.1, None, X, y)
+        dt = time.perf_counter() - t0
+        rows.append({"n": ns, "seconds": dt, "gflops": fit_flops(ns, d) / dt * 1e-9})
+    p = float(np.polyfit(np.log([r["n"] for r in rows]), np.log([r["seconds"] for r in rows]), 1)[0])
+    return rows, p
+
+
 def run_reference(args, rank, world):
     """The reference arm.  friedrich is a Rust crate and this image has no cargo/rustc, so `oracle/_ref` cannot exist;
-    the arm times the oracle port (the reference's algorithm, single-threaded like the crate) on the host CPU."""
+    the arm times the oracle port (the reference's algorithm, single-threaded like the crate) on the host CPU.  `config`
+    is the workload of our arm (same object); each timed step is a BOUNDED SAMPLE of it, described in `sample`."""
     if rank != 0:
         return
-    n, d, q, _, desc = WORKLOADS[args.workload]
-    ns, qs = 2048, 256  # bounded sample of the workload: ~1 s per step
+    n, d, q, config = workload_config(args.workload, world, world > 1)
+    ns, qs = 2048, 256  # bounded sample of the workload: ~1.5 s per step
     dt, flops = time_oracle(ns, d, qs, args.steps, args.warmup)
     val = flops / dt * 1e-12
+    rows, p = cpu_port_scaling(d, (1024, 2048, 4096))
+    t_last, n_last = rows[-1]["seconds"], rows[-1]["n"]
+    sample = (f"oracle fit n={ns} d={d} + predict_mean_variance q={qs} per step, 1 thread (the crate is single-threaded); "
+              f"value = flop rate of the sample on the same algorithmic count")
     line = {
         "impl": "reference", "metric": "gp_fit_tflops", "value": val, "unit": "TFLOP/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "n": n, "d": d, "q": q},
-        "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": 1, "kind": "port",
-                         "sample": f"oracle fit n={ns} d={d} + predict_mean_variance q={qs} per step "
-                                   f"(flop rate; the full n={n} fit would take ~{(n / ns) ** 3 * dt / 60:.0f} min)"},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak" if args.workload == "metric" else "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+        "sample": {"n": ns, "q": qs, "d": d, "what": sample},
+        "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": 1, "kind": "port", "sample": sample,
+                         "fit_seconds_by_n": rows, "fitted_exponent": p,
+                         "extrapolated_fit_seconds_full_config": t_last * (n / n_last) ** 3,
+                         "extrapolation": f"t(n={n}) = t(n={n_last}) x (n/{n_last})^3; measured exponent over the sizes above: {p:.2f}"},
         "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "host_cores": os.cpu_count(),
@@ -164,6 +206,18 @@ def run_reference(args, rank, world):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+
+def workload_config(workload, world, use_sharded, lookahead=True):
+    """The `config` object of the JSON line — built in ONE place so that both arms print the same thing."""
+    n, d, q, _, desc = WORKLOADS[workload]
+    if world > 1 and workload == "metric":
+        n = weak_n(world)
+        desc = f"fit: Gram+Cholesky n={n} d={d} SquaredExp f64 sharded over {world} GPUs (n = 16384*N^(1/3)); predict q={q}"
+    return n, d, q, {"workload": desc, "n": n, "d": d, "q": q, "noise": 0.1, "kernel": "SquaredExp(ls=sqrt(d/6), ampl=1)",
+                     "l2": "inputs larger than L2 (factor = %.2f GB)" % (8.0 * n * n / 1e9),
+                     "multi_gpu": ("block-cyclic 512-column panels, NCCL panel broadcast, replicated factor; queries sharded")
+                     if use_sharded else "single GPU", "lookahead": lookahead}
+
 
 def weak_n(world):
     """Weak scaling: per-GPU Cholesky work n^3/(3N) stays that of n=16384 on one GPU; n is rounded to a whole panel
@@ -183,15 +237,13 @@ def run_ours(args, rank, local_rank, world):
     from friedrich_b200.kernels import SquaredExp
     from friedrich_b200.synthetic import make_dataset, make_inputs
 
-    n, d, q, _, desc = WORKLOADS[args.workload]
     use_sharded = world > 1 or args.sharded
-    if world > 1 and args.workload == "metric":
-        n = weak_n(world)
-        desc = f"fit: Gram+Cholesky n={n} d={d} SquaredExp f64 sharded over {world} GPUs (n = 16384*N^(1/3)); predict q={q}"
+    n, d, q, config = workload_config(args.workload, world, use_sharded, not args.no_lookahead)
     lib = N.lib()
     h = N.Handle(local_rank)
     if use_sharded:
         sharded.comm_init(h, rank, world, dist)
+    noise = 0.1
     Xs, ys = make_dataset(0x5EED0001, n, d)
     qr = q // world  # queries are independent: each rank predicts its slice against the replicated factor
     Xqs = make_inputs(0x5EED0002, q, d)[rank * qr:(rank + 1) * qr]
@@ -331,23 +383,98 @@ def run_ours(args, rank, local_rank, world):
     clocks = sampler.stop()
     bcast_mb = lib.fgp_comm_last_bytes(h.ptr) / 1e6 if use_sharded else 0.0
 
+    # ---- parity of what was just timed (outside every timed region) -----------------------------------------------------
+    def digest(handle):
+        out = np.zeros(3)
+        handle.check(lib.fgp_factor_digest(handle.ptr, N.dptr(out)))
+        return out
+
+    def all_ranks_equal(v):
+        if dist is None:
+            return True
+        import torch
+        lo, hi = torch.tensor(v), torch.tensor(v)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        return bool(torch.equal(lo, hi))
+
+    refit()
+    dg = digest(h)
+    parity = {"factor_digest": [float(v) for v in dg], "digest_equal_across_ranks": all_ranks_equal(dg)}
+    # K alpha = y on probe rows: rows of K recomputed on the host with numpy (independent of the library and of the oracle)
+    alpha = np.zeros(n)
+    h.check(lib.fgp_download_alpha(h.ptr, N.dptr(alpha)))
+    idx = np.random.default_rng(1234).choice(n, 32, replace=False)
+    ls2 = d / 6.0
+    d2 = ((Xs[idx] ** 2).sum(1)[:, None] + (Xs ** 2).sum(1)[None, :] - 2.0 * Xs[idx] @ Xs.T).clip(min=0.0)
+    Krows = np.exp(-d2 / (2.0 * ls2))
+    Krows[np.arange(32), idx] = 1.0 + noise ** 2
+    parity["solve_residual_max"] = float(np.abs(Krows @ alpha - ys[idx]).max())
+    parity["solve_residual_what"] = "max |K[rows] alpha - y[rows]| on 32 probe rows, K rows recomputed on the host (numpy)"
+    parity["alpha_equal_across_ranks"] = all_ranks_equal(alpha[idx].copy())
+    if use_sharded and world > 1 and rank == 0:
+        # the same fit on ONE GPU: a second handle on rank 0's device, factor digests compared bit for bit
+        h1 = N.Handle(local_rank)
+        h1.check(lib.fgp_fit(h1.ptr, N.dptr(X), n, n, d, N.dptr(y), C.byref(kd), noise, 0, 0.0))
+        d1 = digest(h1)
+        single_ms = h1.last_device_ms()
+        parity["bitwise_equal_to_single_gpu_fit"] = bool(np.array_equal(d1, dg))
+        parity["single_gpu_digest_rel_diff"] = float(np.abs(d1 - dg).max() / np.abs(d1).max())
+        parity["single_gpu_same_n_ms"] = single_ms
+        h1.close()
+    barrier()
+
+    # ---- the north star's strong-scaling experiment (C4: n = 32768, d = 32) beside the weak-scaling series ---------------
+    strong = None
+    if world > 1 and args.workload == "metric" and not args.no_strong:
+        n4, d4 = WORKLOADS["c4"][0], WORKLOADS["c4"][1]
+        X4s, y4s = make_dataset(0x5EED0004, n4, d4)
+        kd4 = SquaredExp(math.sqrt(d4 / 6.0), 1.0).device_desc()
+        X4 = np.asfortranarray(X4s)
+        h.check(lib.fgp_fit_sharded(h.ptr, N.dptr(X4) if rank == 0 else None, n4, n4, d4, N.dptr(y4s) if rank == 0 else None,
+                                    C.byref(kd4), noise, 0, 0.0))
+        barrier()
+        ms4 = 0.0
+        for _ in range(2):
+            h.check(lib.fgp_refit_sharded(h.ptr, C.byref(kd4), noise, 0, 0.0))
+            ms4 += h.last_device_ms()
+        ms4 = max_over_ranks(ms4 / 2)
+        dg4 = digest(h)
+        eq4 = all_ranks_equal(dg4)
+        one_ms = None
+        if rank == 0:  # the 1-GPU time of the same problem, measured in this run on rank 0's GPU while the others wait
+            h1 = N.Handle(local_rank)
+            h1.check(lib.fgp_fit(h1.ptr, N.dptr(X4), n4, n4, d4, N.dptr(y4s), C.byref(kd4), noise, 0, 0.0))
+            h1.check(lib.fgp_refit(h1.ptr, C.byref(kd4), noise, 0, 0.0))
+            one_ms = h1.last_device_ms()
+            h1.close()
+        barrier()
+        if rank == 0:
+            f4 = fit_flops(n4, d4)
+            strong = {"config": "C4: RBF n=32768 d=32 fit (Gram + Cholesky), strong scaling", "n": n4, "d": d4, "n_gpus": world,
+                      "ms_per_step": ms4, "tflops": f4 / (ms4 * 1e-3) * 1e-12, "one_gpu_ms_same_run": one_ms,
+                      "one_gpu_tflops_same_run": f4 / (one_ms * 1e-3) * 1e-12, "speedup": one_ms / ms4,
+                      "efficiency": one_ms / ms4 / world, "frac_of_fp64_peak": f4 / (ms4 * 1e-3) * 1e-12 / (world * FP64_PEAK_TFLOPS),
+                      "digest_equal_across_ranks": eq4}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
     value = fit_flops(n, d) / (fit_ms * 1e-3) * 1e-12
+    traffic, traffic_launches, traffic_file = gemm_traffic_bytes_per_launch(args.workload) if world == 1 else (None, 0, None)
+    traffic_src = (f"{traffic_file}: dram__bytes_read.sum + dram__bytes_write.sum over the {traffic_launches} gemm_nt launches of one "
+                   f"fit of this build / launches") if traffic else "no ncu DRAM capture of this build committed for this workload"
     gemm_tflops = tfl[0] / (tms[0] * 1e-3) * 1e-12 if tms[0] > 0 else None
     line = {
         "metric": "gp_fit_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": fit_ms, "higher_is_better": True,
-        "scaling": "weak" if (world > 1 and args.workload == "metric") else "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": desc, "n": n, "d": d, "q": q, "noise": noise, "kernel": "SquaredExp(ls=sqrt(d/6), ampl=1)",
-                   "l2": "inputs larger than L2 (factor = %.2f GB)" % (8.0 * n * n / 1e9),
-                   "multi_gpu": ("block-cyclic 512-column panels, NCCL panel broadcast slab by slab, replicated factor; "
-                                 "queries sharded") if use_sharded else "single GPU",
-                   "lookahead": not args.no_lookahead},
+        # the --gpus N series of the metric workload is a WEAK-scaling series (n = 16384 N^(1/3): equal Cholesky work per GPU)
+        # whose N = 1 point is the metric's own configuration; the strong-scaling experiment of the north star (C4) is the
+        # `strong_c4` block of every N > 1 line
+        "scaling": "weak" if args.workload == "metric" else "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config,
         "frac_of_fp64_peak": value / (world * FP64_PEAK_TFLOPS),
         "predict_qps": q / (pred_ms * 1e-3), "predict_ms": pred_ms, "predict_q1_latency_ms": q1_ms,
         "wall_ms_per_step": wall_ms / args.steps,
@@ -360,7 +487,7 @@ def run_ours(args, rank, local_rank, world):
         "gpu_launches": int(launches),
         "roofline": {"kernel": "gemm_nt_kernel", "bound": "tensor", "achieved": gemm_tflops, "peak": FP64_PEAK_TFLOPS,
                      "unit": "TFLOP/s", "frac": (gemm_tflops / FP64_PEAK_TFLOPS) if gemm_tflops else None,
-                     "traffic": GEMM_TRAFFIC_BYTES_PER_LAUNCH.get(args.workload) if world == 1 else None,
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "launches": int(tcnt[0]), "share_of_step": float(tms[0] / max(prof_dev_ms, 1e-9)),
                      "note": "rank 0; achieved = algorithmic flops of ALL gemm_nt launches of a fit (from the 56-wave trailing "
                              "updates down to sub-wave panel products) / sum of their CUDA-event durations, from a separate "
@@ -371,21 +498,36 @@ def run_ours(args, rank, local_rank, world):
                      "peak_source": "fp64 DMMA m8n8k4 register-resident burst measured on this pool "
                                     "(profiles/fp64_peak_r01.jsonl; MEASURED_PEAKS.json has no fp64 figure; nominal "
                                     "148 SM x 128 flop/clk x 1.965 GHz = 37.2; sustained DMMA loop 27.4)"},
-        "kernel_ms_per_step": {"gemm_nt": tms[0] / args.steps, "potrf_diag": tms[1] / args.steps,
+        "kernel_ms_per_step": {"gemm_nt": tms[0] / args.steps, "potrf_head": tms[1] / args.steps,
                                "gram": tms[2] / args.steps},
+        # what bounds a step: summed kernel time per class from the profiling pass (on one GPU: single-stream schedule, so
+        # the sum IS the step) next to the overlapped step; the head kernels are the serial chain, the rest is GEMM
+        "step_breakdown_ms": {"overlapped_step": fit_ms, "serialised_step": prof_dev_ms / max(args.steps, 1),
+                              "gemm": tms[0] / args.steps, "panel_heads": tms[1] / args.steps, "gram": tms[2] / args.steps,
+                              "bcast_as_owner": (tms[3] / args.steps) if use_sharded else 0.0,
+                              "panel_head_launches": int(tcnt[1] // max(args.steps, 1))},
+        "parity": parity,
         "bcast_as_owner": ({"ms_per_step": tms[3] / args.steps, "launches": int(tcnt[3]),
                             "GBps": (tfl[3] / max(tms[3], 1e-9)) * 1e-6} if use_sharded and tcnt[3] else None),
         "clocks": clocks,
     }
     if use_sharded:
         line["nccl_bcast_mb_per_step"] = bcast_mb
+    if strong is not None:
+        line["strong_c4"] = strong
     if world == 1 and not args.no_cpu_baseline:
         ns, qs = (4096, 256) if n >= 4096 else (n, min(q, 256))
         dt, flops = time_oracle(ns, d, qs, 1, 0)
+        rows, pexp = cpu_port_scaling(d, (1024, 2048))
+        rows.append({"n": ns, "seconds": dt, "gflops": flops / dt * 1e-9, "note": f"includes predict q={qs}"})
         line["cpu_baseline"] = {"value": flops / dt * 1e-12, "unit": "TFLOP/s", "cores": 1, "kind": "port",
                                 "host_cores": os.cpu_count(), "seconds": dt,
                                 "sample": f"oracle fit n={ns} d={d} + predict_mean_variance q={qs}, 1 step, 1 thread "
-                                          f"(the reference is single-threaded)"}
+                                          f"(the reference is single-threaded)",
+                                "fit_seconds_by_n": rows, "fitted_exponent_1024_2048": pexp,
+                                "extrapolated_fit_seconds_full_config": dt * (n / ns) ** 3,
+                                "extrapolation": f"t(n={n}) = t(n={ns}) x (n/{ns})^3 (the rate falls out of cache above n~3000, "
+                                                 f"so the cubic law is a lower bound on the CPU time)"}
     print(json.dumps(line), flush=True)
     for p in (pX, py, pq, pm, pv):
         lib.fgp_free_pinned(p)
@@ -404,6 +546,7 @@ def main():
     ap.add_argument("--no-lookahead", action="store_true", help="A/B: single-stream Cholesky schedule")
     ap.add_argument("--no-profile", action="store_true", help="A/B: no per-launch CUDA events (roofline fields become null)")
     ap.add_argument("--sharded", action="store_true", help="use the collective entry points even on one GPU")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling C4 block")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

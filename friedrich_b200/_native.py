@@ -18,6 +18,7 @@ MAX_OPS = 15
 MAX_PARAMS = 24
 
 FGP_OPT_LOOKAHEAD = 1
+FGP_OPT_HEAD = 2
 FGP_COMM_ID_BYTES = 128
 FGP_OK, FGP_ERR_NOT_POSDEF, FGP_ERR_BAD_ARG, FGP_ERR_BAD_KERNEL, FGP_ERR_CUDA, FGP_ERR_NOT_FITTED, FGP_ERR_COMM = range(7)
 
@@ -77,6 +78,7 @@ SIGNATURES = {
     "fgp_mean_pair_distance": (C.c_int, [_h, _dp]),
     "fgp_download_factor": (C.c_int, [_h, _dp, _i64]),
     "fgp_download_alpha": (C.c_int, [_h, _dp]),
+    "fgp_factor_digest": (C.c_int, [_h, _dp]),
     "fgp_upload_state": (C.c_int, [_h, _dp, _i64, _i64, _i64, _dp, _dp, _i64]),
     "fgp_inverse_columns": (C.c_int, [_h, C.POINTER(_i64), _i64, _dp, _i64]),
     "fgp_last_device_ms": (C.c_double, [_h]),
@@ -98,6 +100,9 @@ SIGNATURES = {
     "fgp_free_pinned": (None, [C.c_void_p]),
     "fgp_cholesky_lower": (C.c_int, [C.c_int, _dp, _i64, _i64, C.POINTER(_i64)]),
     "fgp_dbg_lower_tiles": (_i64, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _i64]),
+    "fgp_dbg_lower_tiles_skip": (_i64, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                        _i64]),
+    "fgp_dbg_potrf_head": (C.c_int, [C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_double, C.POINTER(C.c_int), C.c_int, _dp]),
     "fgp_dbg_exp": (C.c_double, [C.c_double]),
     "fgp_dbg_gemm_occupancy": (C.c_int, [C.c_int]),
     "fgp_dbg_gemm_occupancy32": (C.c_int, [C.c_int]),

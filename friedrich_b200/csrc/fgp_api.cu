@@ -72,8 +72,38 @@ void solve_alpha(fgp_model* m) {
     m->launches += 2;
 }
 
-// hook for whatever the blocked factorisation caches per panel on top of inv / invT (nothing yet)
-int rebuild_panel_inverses(fgp_model*) { return FGP_OK; }
+// The per-panel inverse blocks W are only read inside the factorisation that produces them, so a restored factor
+// (fgp_upload_state) needs none: the panel table is simply emptied.
+int rebuild_panel_inverses(fgp_model* m) {
+    m->pstart.clear();
+    return FGP_OK;
+}
+
+// Buffers of the head schedule for factoring block columns [jb_begin, np/128): the panel table keeps the panels that start
+// before jb_begin (a panel cut by jb_begin stays valid: the leading block of a triangular inverse is the inverse of the
+// leading block), the new ones follow.  *p0 = W / sync slot of the first new panel.
+int prepare_head_work(fgp_model* m, int64_t jb_begin, PotrfWork* w, int64_t* p0) {
+    const int64_t nb = m->np / TILE, PT = HEAD_PANEL / TILE;
+    while (!m->pstart.empty() && m->pstart.back() >= jb_begin) m->pstart.pop_back();
+    *p0 = (int64_t)m->pstart.size();
+    for (int64_t J = jb_begin; J < nb; J += PT) m->pstart.push_back(J);
+    const int64_t slots = (int64_t)m->pstart.size();
+    CU(m, m->Wp.reserve((size_t)slots * HEAD_PANEL * HEAD_PANEL, true, m->st, true));  // diagonal tiles: lower triangles written only
+    CU(m, m->Pscr.reserve((size_t)HEAD_PANEL * HEAD_PANEL));
+    CU(m, m->pbuf[0].reserve((size_t)m->cap * HEAD_PANEL));
+    CU(m, m->pbuf[1].reserve((size_t)m->cap * HEAD_PANEL));
+    if (slots > m->head_sync_cap) {
+        if (m->head_sync) cudaFree(m->head_sync);
+        m->head_sync = nullptr;
+        m->head_sync_cap = 0;
+        const int64_t cap = std::max<int64_t>(2 * slots, 64);
+        CU(m, cudaMalloc(&m->head_sync, (size_t)cap * HEAD_SYNC_INTS * sizeof(int)));
+        m->head_sync_cap = cap;
+    }
+    *w = PotrfWork{m->inv.p, m->invT.p, m->Wp.p, m->Pscr.p, m->head_sync, {m->pbuf[0].p, m->pbuf[1].p}, m->evTop, m->evRest,
+                   {m->evCopy[0], m->evCopy[1]}};
+    return FGP_OK;
+}
 
 int reserve_training(fgp_model* m, int64_t cap_rows, int64_t dp, bool keep) {
     // `keep` is used by add_samples when the capacity grows: point arrays and vectors keep their prefix; L is handled by
@@ -87,7 +117,7 @@ int reserve_training(fgp_model* m, int64_t cap_rows, int64_t dp, bool keep) {
     CU(m, m->z.reserve((size_t)cap_rows));
     CU(m, m->alpha.reserve((size_t)cap_rows));
     CU(m, m->work.reserve((size_t)cap_rows));
-    CU(m, m->inv.reserve((size_t)cap_rows * TILE, keep, m->st));
+    CU(m, m->inv.reserve((size_t)cap_rows * TILE, keep, m->st, true));  // the head kernel writes the lower triangles only
     CU(m, m->invT.reserve((size_t)cap_rows * TILE, keep, m->st));
     return FGP_OK;
 }
@@ -113,13 +143,25 @@ int factor_resident(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits&
     };
     PotrfCounters cnt;
     const PotrfLookahead la{m->st2, m->evA, m->evB, m->st3, m->evC, m->evD};
-    potrf_lower(m->L.p, m->cap, m->np, 0, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->ctx(), m->lookahead ? &la : nullptr,
-                &cnt, &rest);
+    if (m->head_schedule) {
+        PotrfWork w;
+        int64_t p0 = 0;
+        FGP_TRY(prepare_head_work(m, 0, &w, &p0));
+        potrf_lower_head(m->L.p, m->cap, m->np, 0, w, p0, has_eps, eps, m->info_d, m->ctx(), m->lookahead ? &la : nullptr, &cnt,
+                         &rest);
+    } else {
+        potrf_lower(m->L.p, m->cap, m->np, 0, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->ctx(),
+                    m->lookahead ? &la : nullptr, &cnt, &rest);
+    }
     m->launches += cnt.launches;
     CU(m, cudaMemcpyAsync(m->info_h, m->info_d, sizeof(int), cudaMemcpyDeviceToHost, m->st));
     solve_alpha(m);
     CU(m, cudaStreamSynchronize(m->st));
     CU(m, cudaGetLastError());
+    if (*m->info_h == HEAD_TIMEOUT) {
+        m->fitted = false;
+        return fail(m, FGP_ERR_CUDA, "internal error: a dependency wait inside potrf_head_kernel timed out");
+    }
     if (*m->info_h != 0) {
         m->failed_col = *m->info_h - 1;
         m->fitted = false;
@@ -325,6 +367,11 @@ FGP_EXPORT int fgp_create(int device, fgp_model** out) {
               cudaEventCreate(&m->ev0) == cudaSuccess && cudaEventCreate(&m->ev1) == cudaSuccess &&
               cudaEventCreateWithFlags(&m->evA, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&m->evB, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&m->evTop, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&m->evRest, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&m->evCopy[0], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&m->evCopy[1], cudaEventDisableTiming) == cudaSuccess &&
+              potrf_head_prepare() == cudaSuccess &&
               cudaMalloc(&m->info_d, sizeof(int)) == cudaSuccess &&
               cudaMallocHost(&m->info_h, sizeof(int)) == cudaSuccess && potrf_prepare() == cudaSuccess;
     if (!ok) {
@@ -346,8 +393,12 @@ FGP_EXPORT int fgp_destroy(fgp_model* m) {
         comm_release(m);
         for (DevBuf* b : {&m->xr, &m->xc, &m->nc, &m->nr, &m->cmean, &m->y, &m->z, &m->alpha, &m->work, &m->L, &m->inv,
                           &m->invT, &m->staging, &m->qr, &m->qc, &m->qnc, &m->qnr, &m->bt, &m->partial, &m->mean_d,
-                          &m->var_d, &m->scalars, &m->kqq, &m->U, &m->Kinv, &m->lml_partial})
+                          &m->var_d, &m->scalars, &m->kqq, &m->U, &m->Kinv, &m->lml_partial, &m->Wp, &m->Pscr, &m->pbuf[0],
+                          &m->pbuf[1]})
             b->release();
+        if (m->head_sync) cudaFree(m->head_sync);
+        for (cudaEvent_t e : {m->evTop, m->evRest, m->evCopy[0], m->evCopy[1]})
+            if (e) cudaEventDestroy(e);
         if (m->info_d) cudaFree(m->info_d);
         if (m->info_h) cudaFreeHost(m->info_h);
         if (m->pinned) cudaFreeHost(m->pinned);
@@ -385,6 +436,7 @@ FGP_EXPORT int fgp_set_option(fgp_model* m, int option, int64_t value) {
     std::lock_guard<std::mutex> lk(m->mu);
     switch (option) {
         case FGP_OPT_LOOKAHEAD: m->lookahead = value != 0; return FGP_OK;
+        case FGP_OPT_HEAD: m->head_schedule = value != 0; return FGP_OK;
         default: return fail(m, FGP_ERR_BAD_ARG, "unknown option");
     }
 }
@@ -683,6 +735,57 @@ __global__ void gather_sym_columns_kernel(const double* __restrict__ Kinv, int64
 }
 }  // namespace
 
+namespace {
+// Deterministic digest of the lower triangle of the factor: per column c (one CTA, fixed-order tree), three sums
+//   d0 = sum L[r,c]      d1 = sum L[r,c]^2      d2 = sum L[r,c] * w(r,c),  w = ((31 r + 17 c) mod 1009) + 1
+// then one thread folds the columns in order.  Bitwise-equal factors give bitwise-equal digests (and a single differing
+// element changes d2 with overwhelming probability): cross-rank / sharded-vs-single comparisons without moving 8 n^2 bytes.
+__global__ void __launch_bounds__(256) digest_columns_kernel(const double* __restrict__ L, int64_t ld, int64_t n, double* partial) {
+    __shared__ double red[3][256];
+    const int64_t c = blockIdx.x;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int64_t r = c + threadIdx.x; r < n; r += 256) {
+        const double v = L[r + c * ld];
+        s0 += v;
+        s1 = fma(v, v, s1);
+        s2 = fma(v, (double)((31 * r + 17 * c) % 1009 + 1), s2);
+    }
+    red[0][threadIdx.x] = s0; red[1][threadIdx.x] = s1; red[2][threadIdx.x] = s2;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+            for (int k = 0; k < 3; ++k) red[k][threadIdx.x] += red[k][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) partial[c * 3 + threadIdx.x] = red[threadIdx.x][0];
+}
+__global__ void digest_final_kernel(const double* __restrict__ partial, int64_t n, double* out) {
+    if (threadIdx.x < 3) {
+        double s = 0.0;
+        for (int64_t c = 0; c < n; ++c) s += partial[c * 3 + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+}
+}  // namespace
+
+// out[0..2] = (sum, sum of squares, position-weighted sum) over the lower triangle of the resident factor; deterministic.
+FGP_EXPORT int fgp_factor_digest(fgp_model* m, double* out) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (!m->fitted) return fail(m, FGP_ERR_NOT_FITTED, "model is not fitted");
+    if (!out) return fail(m, FGP_ERR_BAD_ARG, "null output");
+    CU(m, m->staging.reserve((size_t)3 * m->n + 8));
+    digest_columns_kernel<<<(unsigned)m->n, 256, 0, m->st>>>(m->L.p, m->cap, m->n, m->staging.p);
+    digest_final_kernel<<<1, 32, 0, m->st>>>(m->staging.p, m->n, m->staging.p + 3 * m->n);
+    FGP_TRY(ensure_pinned(m, 8));
+    CU(m, cudaMemcpyAsync(m->pinned, m->staging.p + 3 * m->n, 3 * sizeof(double), cudaMemcpyDeviceToHost, m->st));
+    CU(m, cudaStreamSynchronize(m->st));
+    CU(m, cudaGetLastError());
+    for (int i = 0; i < 3; ++i) out[i] = m->pinned[i];
+    return FGP_OK;
+}
+
 // Restore a handle from a serialised model (serde round trip of GaussianProcess, mod.rs:58; EMatrix / EVector
 // extendable_matrix.rs:14,62; nalgebra's Cholesky keeps the full n x n matrix with the factor in its lower triangle):
 // training inputs, residual outputs and the factor go back to the device WITHOUT refitting; what the device path caches on
@@ -783,12 +886,20 @@ FGP_EXPORT int fgp_add_samples(fgp_model* m, const double* Xnew, int64_t ldx, in
                               m->ctx());
     PotrfCounters cnt;
     const PotrfLookahead la{m->st2, m->evA, m->evB, m->st3, m->evC, m->evD};
-    potrf_lower(m->L.p, m->cap, np_new, jb, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->ctx(), m->lookahead ? &la : nullptr,
-                &cnt);
+    if (m->head_schedule) {
+        PotrfWork w;
+        int64_t p0 = 0;
+        FGP_TRY(prepare_head_work(m, jb, &w, &p0));
+        potrf_lower_head(m->L.p, m->cap, np_new, jb, w, p0, has_eps, eps, m->info_d, m->ctx(), m->lookahead ? &la : nullptr, &cnt);
+    } else {
+        potrf_lower(m->L.p, m->cap, np_new, jb, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->ctx(),
+                    m->lookahead ? &la : nullptr, &cnt);
+    }
     m->launches += cnt.launches;
     CU(m, cudaMemcpyAsync(m->info_h, m->info_d, sizeof(int), cudaMemcpyDeviceToHost, m->st));
     solve_alpha(m);
     int rc2 = end_timed(m);
+    if (rc2 == FGP_OK && *m->info_h == HEAD_TIMEOUT) rc2 = fail(m, FGP_ERR_CUDA, "internal error: a dependency wait inside potrf_head_kernel timed out");
     if (rc2 != FGP_OK || *m->info_h != 0) {
         // The block rows from jb on (old rows of the last partial tile included) have been rebuilt and are now garbage: the
         // handle goes back to the OLD sample count and needs a full refit (fgp_refit / fgp_fit), which the resident inputs
@@ -1032,13 +1143,73 @@ FGP_EXPORT int fgp_refit_sharded(fgp_model* m, const fgp_kernel_desc* kernel, do
 
 // =================================================================================================================
 // test hook (host only, no GPU): the block -> tile map of the lower-mode GEMM launches, see gemm_tile_decode
-FGP_EXPORT int64_t fgp_dbg_lower_tiles(int M, int N, int grp, int stride, int* ti_out, int* tj_out, int64_t capacity) {
+FGP_EXPORT int64_t fgp_dbg_lower_tiles_skip(int M, int N, int grp, int stride, int row_skip, int* ti_out, int* tj_out,
+                                            int64_t capacity) {
     GemmArgs g{};
-    g.M = M; g.N = N; g.K = GEMM_KC; g.lower = 1; g.grp = grp; g.stride = stride;
+    g.M = M; g.N = N; g.K = GEMM_KC; g.lower = 1; g.grp = grp; g.stride = stride; g.row_skip = row_skip;
     const int64_t tiles = gemm_nt_tiles(g);
     gemm_nt_plan(g);
     for (int64_t b = 0; b < tiles && b < capacity; ++b) gemm_tile_decode(g, (int)b, ti_out[b], tj_out[b]);
     return tiles;
+}
+FGP_EXPORT int64_t fgp_dbg_lower_tiles(int M, int N, int grp, int stride, int* ti_out, int* tj_out, int64_t capacity) {
+    return fgp_dbg_lower_tiles_skip(M, N, grp, stride, 0, ti_out, tj_out, capacity);
+}
+
+// =================================================================================================================
+// test hook: the panel head kernel alone on a host matrix.  A: (128 nt)^2 column-major SPD (lower read) -> L in place (lower);
+// W: (128 nt)^2 (ld = 128 nt) <- L^-1 (lower block triangle; strict upper blocks zeroed).  *info_out = the kernel's info word.
+FGP_EXPORT int fgp_dbg_potrf_head(int device, double* A, int nt, double* W, int has_sub, double sub, int* info_out, int reps,
+                                  double* ms_out) {
+    if (!A || !W || nt < 1 || nt > HEAD_PANEL / TILE) return FGP_ERR_BAD_ARG;
+    DeviceGuard dg(device);
+    if (potrf_head_prepare() != cudaSuccess) return FGP_ERR_CUDA;
+    const int64_t n = (int64_t)nt * TILE;
+    double *dA = nullptr, *dinv = nullptr, *dW = nullptr, *dP = nullptr;
+    int *dsync = nullptr, *dinfo = nullptr;
+    int rc = FGP_OK;
+    if (cudaMalloc(&dA, n * n * 8) != cudaSuccess || cudaMalloc(&dinv, n * TILE * 8) != cudaSuccess ||
+        cudaMalloc(&dW, HEAD_PANEL * HEAD_PANEL * 8) != cudaSuccess || cudaMalloc(&dP, HEAD_PANEL * HEAD_PANEL * 8) != cudaSuccess ||
+        cudaMalloc(&dsync, HEAD_SYNC_INTS * 4) != cudaSuccess || cudaMalloc(&dinfo, 4) != cudaSuccess)
+        rc = FGP_ERR_CUDA;
+    if (rc == FGP_OK) {
+        cudaMemcpy(dA, A, n * n * 8, cudaMemcpyHostToDevice);
+        cudaMemset(dW, 0, HEAD_PANEL * HEAD_PANEL * 8);
+        cudaMemset(dsync, 0, HEAD_SYNC_INTS * 4);
+        cudaMemset(dinfo, 0, 4);
+        launch_potrf_head(dA, n, nt, dinv, dW, dP, dsync, has_sub, sub, dinfo, 0, LaunchCtx{});
+        if (cudaDeviceSynchronize() != cudaSuccess) rc = FGP_ERR_CUDA;
+        if (ms_out && reps > 0 && rc == FGP_OK) {  // timing: the same launch on a fresh copy of A, CUDA events around the kernel only
+            double* dA2 = nullptr;
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            if (cudaMalloc(&dA2, n * n * 8) == cudaSuccess) {
+                float total = 0.f;
+                for (int r = 0; r < reps; ++r) {
+                    cudaMemcpy(dA2, A, n * n * 8, cudaMemcpyHostToDevice);
+                    cudaMemset(dsync, 0, HEAD_SYNC_INTS * 4);
+                    cudaEventRecord(e0, nullptr);
+                    launch_potrf_head(dA2, n, nt, dinv, dW, dP, dsync, has_sub, sub, dinfo, 0, LaunchCtx{});
+                    cudaEventRecord(e1, nullptr);
+                    cudaEventSynchronize(e1);
+                    float t = 0.f;
+                    cudaEventElapsedTime(&t, e0, e1);
+                    total += t;
+                }
+                *ms_out = total / reps;
+                cudaFree(dA2);
+            }
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+        }
+        cudaMemcpy(A, dA, n * n * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy2D(W, n * 8, dW, HEAD_PANEL * 8, n * 8, n, cudaMemcpyDeviceToHost);
+        if (info_out) cudaMemcpy(info_out, dinfo, 4, cudaMemcpyDeviceToHost);
+    }
+    for (void* q : {(void*)dA, (void*)dinv, (void*)dW, (void*)dP, (void*)dsync, (void*)dinfo}) cudaFree(q);
+    if (cudaGetLastError() != cudaSuccess) rc = FGP_ERR_CUDA;
+    return rc;
 }
 
 // =================================================================================================================
@@ -1059,6 +1230,18 @@ FGP_EXPORT int fgp_dbg_gemm_occupancy32(int device) {
     return gemm_nt_occupancy(32);
 }
 
+namespace {
+__global__ void fill_random_kernel(double* p, int64_t n, uint64_t seed) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);  // splitmix64
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        p[i] = (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+    }
+}
+}  // namespace
+
 FGP_EXPORT int fgp_dbg_gemm_bench(int device, int M, int N, int K, int lower, int beta_one, int reps, double* ms_out,
                                   double* flops_out) {
     if (M % GEMM_BM || N % GEMM_BN || K % GEMM_KC || reps < 1 || !ms_out) return FGP_ERR_BAD_ARG;
@@ -1071,8 +1254,9 @@ FGP_EXPORT int fgp_dbg_gemm_bench(int device, int M, int N, int K, int lower, in
         cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)
         rc = FGP_ERR_CUDA;
     if (rc == FGP_OK) {
-        cudaMemset(dC, 0, (size_t)M * N * 8);
-        cudaMemset(dA, 0, (size_t)M * K * 8);
+        // random operands in [-1, 1): all-zero matrices would not toggle the datapath like real panels do
+        fill_random_kernel<<<1024, 256>>>(dC, (int64_t)M * N, 0x9E3779B97F4A7C15ull);
+        fill_random_kernel<<<1024, 256>>>(dA, (int64_t)M * K, 0xD1B54A32D192ED03ull);
         GemmArgs g{};
         g.C = dC; g.ldc = M;
         g.A = dA; g.lda = M;

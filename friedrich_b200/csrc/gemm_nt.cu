@@ -52,7 +52,8 @@ gemm_nt_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ CUten
     const int sub = blockIdx.x % S::SUBS;
     const int m0 = ti * GEMM_BM + sub * CM, n0 = tj * GEMM_BN;
     const int kbeg = g.k_from_tile ? GEMM_BM * max(ti, tj) : 0;
-    const int nk = (g.K - kbeg) / GEMM_KC;
+    const int kend = g.k_upto_col ? min(g.K, GEMM_BN * (tj + 1)) : g.K;
+    const int nk = (kend - kbeg) / GEMM_KC;
     const bool diag_tile = g.lower && (ti == tj);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -260,17 +261,19 @@ void gemm_nt_plan(GemmArgs& g) {
     if (!g.lower) return;
     const int tm = g.M / GEMM_BM, tn = g.N / GEMM_BN;
     const int PT = std::max(g.grp, 1), S = std::max(g.stride, 1);
+    const int skip = std::min(std::max(g.row_skip, 0), tm);
     int R = GEMM_BAND_ROWS;
     while ((tm + R - 1) / R > GEMM_MAX_BANDS) R *= 2;
-    const int nb = std::max(1, (tm + R - 1) / R);
+    const int nb = std::max(1, (tm - skip + R - 1) / R);
     g.band_rows = R;
     g.n_bands = nb;
     std::vector<int64_t> cnt(nb, 0);
-    for (int jl = 0; jl < tn; ++jl) {  // local column jl: tiles tj .. tm-1, spread over bands tj / R .. nb-1
+    for (int jl = 0; jl < tn; ++jl) {  // local column jl: tiles max(tj, skip) .. tm-1, spread over the bands from its first row on
         const int tj = (jl / PT) * S + jl % PT;
         if (tj >= tm) break;
-        for (int r = tj / R; r < nb; ++r) {
-            const int lo = std::max(r * R, tj), hi = std::min(tm, (r + 1) * R);
+        const int first = std::max(tj, skip);
+        for (int r = (first - skip) / R; r < nb; ++r) {
+            const int lo = std::max(skip + r * R, first), hi = std::min(tm, skip + (r + 1) * R);
             cnt[r] += hi - lo;
         }
     }
@@ -288,8 +291,8 @@ int64_t gemm_nt_tiles(const GemmArgs& g) {
     const int64_t PT = std::max(g.grp, 1), S = std::max(g.stride, 1);
     int64_t tiles = 0;
     for (int64_t jl = 0; jl < tn; ++jl) {  // local tile column jl sits at tile column (jl / PT) * S + jl % PT
-        const int64_t tj = (jl / PT) * S + jl % PT;
-        if (tm - tj > 0) tiles += tm - tj;
+        const int64_t tj = (jl / PT) * S + jl % PT, first = std::max<int64_t>(tj, g.row_skip);
+        if (tm - first > 0) tiles += tm - first;
     }
     return tiles;
 }
@@ -300,6 +303,11 @@ double gemm_nt_flops(const GemmArgs& g) {
         double f = 0.0;
         for (int i = 0; i < tm; ++i) f += (double)(i + 1) * (g.K - GEMM_BM * i);
         return 2.0 * GEMM_BM * GEMM_BN * f;
+    }
+    if (g.k_upto_col && !g.lower) {  // A W^T with W lower block-triangular: tile column j contracts over min(K, 128 (j + 1))
+        double f = 0.0;
+        for (int j = 0; j < g.N / GEMM_BN; ++j) f += std::min<double>(g.K, GEMM_BN * (j + 1));
+        return 2.0 * GEMM_BM * GEMM_BN * (g.M / GEMM_BM) * f;
     }
     return 2.0 * GEMM_BM * GEMM_BN * (double)gemm_nt_tiles(g) * g.K;
 }

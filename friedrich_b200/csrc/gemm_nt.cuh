@@ -72,6 +72,9 @@ struct GemmArgs {
                      //    are `stride` tile columns apart (0,0 = contiguous); rows/columns are relative to C, whose origin
                      //    is on the diagonal
     int k_from_tile; // 1: contraction starts at k = 128*max(tile_row, tile_col) (operands upper-triangular: U U^T)
+    int k_upto_col;  // 1: contraction ends at k = 128*(tile_col + 1) (B lower block-triangular: the panel solve A W^T, W = L11^-1)
+    int row_skip;    // lower mode: the first row_skip tile rows are not computed (the diagonal block of the next panel is
+                     //    updated by a separate, earlier launch on the panel stream)
     // filled by gemm_nt_plan (called by gemm_nt_launch): the band rasterisation of lower-mode launches
     int band_rows;                          // tile rows per band
     int n_bands;
@@ -98,7 +101,7 @@ __host__ __device__ inline void gemm_tile_decode(const GemmArgs& g, int b, int& 
     int r = 0;
     while (r + 1 < g.n_bands && g.band_prefix[r + 1] <= b) ++r;
     int o = b - g.band_prefix[r];
-    const int lo = r * R, hi = (lo + R < tm) ? lo + R : tm, h = hi - lo;
+    const int lo = g.row_skip + r * R, hi = (lo + R < tm) ? lo + R : tm, h = hi - lo;
     // local columns entirely above the band (tj < lo) are full-height
     int nf = (lo / S) * PT + ((lo % S) < PT ? (lo % S) : PT);
     if (nf > tn) nf = tn;

@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/fgp.h"
 #include "common.cuh"
@@ -19,15 +20,20 @@ namespace fgp {
 struct DevBuf {
     double* p = nullptr;
     size_t cap = 0;  // in doubles
-    // grow-only; `keep` preserves the old contents (first `cap` doubles)
-    cudaError_t reserve(size_t n, bool keep = false, cudaStream_t st = 0) {
+    // grow-only; `keep` preserves the old contents (first `cap` doubles); `zero` clears whatever is new (buffers whose
+    // never-written parts are read as zeros: the strict upper triangles of the inverse diagonal tiles)
+    cudaError_t reserve(size_t n, bool keep = false, cudaStream_t st = 0, bool zero = false) {
         if (n <= cap) return cudaSuccess;
         double* q = nullptr;
         cudaError_t e = cudaMalloc(&q, n * sizeof(double));
         if (e != cudaSuccess) return e;
-        if (keep && p && cap) {
-            e = cudaMemcpyAsync(q, p, cap * sizeof(double), cudaMemcpyDeviceToDevice, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        const size_t kept = (keep && p) ? cap : 0;
+        if (zero) e = cudaMemsetAsync(q + kept, 0, (n - kept) * sizeof(double), st);
+        if (e == cudaSuccess && kept) e = cudaMemcpyAsync(q, p, kept * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess && (kept || zero)) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            cudaFree(q);
+            return e;
         }
         if (p) cudaFree(p);
         p = q;
@@ -62,6 +68,13 @@ struct fgp_model {
     fgp::DevBuf xr, xc, nc, nr, cmean;     // raw / centred points [cap][dp], squared norms, column means [dp]
     fgp::DevBuf y, z, alpha, work;         // outputs (0 padded), L^-1 y, K^-1 y, scratch vector
     fgp::DevBuf L, inv, invT;              // factor [cap x cap], inverse diagonal blocks and their transposes
+    // head schedule of the blocked Cholesky (potrf.cuh PotrfWork): per-panel inverse blocks W, head scratch, panel buffers
+    fgp::DevBuf Wp, Pscr, pbuf[2];
+    int* head_sync = nullptr;              // [head_sync_cap][HEAD_SYNC_INTS]
+    int64_t head_sync_cap = 0;
+    std::vector<int64_t> pstart;           // first block column of every panel of the current factor (W slot = index)
+    cudaEvent_t evTop = nullptr, evRest = nullptr, evCopy[2] = {nullptr, nullptr};
+    bool head_schedule = true;             // FGP_OPT_HEAD: 0 = the per-block-column schedule of round 1 (A/B runs)
     fgp::DevBuf staging;                   // H2D landing zone (column-major inputs)
     int* info_d = nullptr;
     int* info_h = nullptr;                 // pinned

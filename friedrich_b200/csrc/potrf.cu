@@ -466,4 +466,124 @@ void potrf_lower(double* A, int64_t lda, int64_t np, int64_t jb_begin, double* i
     cudaStreamWaitEvent(st.st, la->ev_panel, 0);  // join: everything after the factorisation runs on M
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// head schedule (contract in potrf.cuh)
+int64_t potrf_lower_head(double* A, int64_t lda, int64_t np, int64_t jb_begin, const PotrfWork& w, int64_t p0, int has_sub,
+                         double sub, int* info, const LaunchCtx& st, const PotrfLookahead* la, PotrfCounters* cnt,
+                         const std::function<void()>* after_first_panel_may_start) {
+    constexpr int64_t PT = HEAD_PANEL / TILE;
+    // below this many rows the whole panel solve is one sub-wave launch on the panel stream (no split into top / rest)
+    constexpr int64_t SOLVE_SPLIT_ROWS = 4096;
+    const int64_t nb = np / TILE;
+    if (jb_begin >= nb) {
+        if (after_first_panel_may_start) (*after_first_panel_may_start)();
+        return 0;
+    }
+    const bool two = la && la->panel;
+    LaunchCtx pc = st, sc = st;
+    if (two) {
+        pc.st = la->panel;
+        sc.st = la->side ? la->side : st.st;
+    }
+    const int64_t npanels = (nb - jb_begin + PT - 1) / PT;
+    cudaMemsetAsync(w.sync + p0 * HEAD_SYNC_INTS, 0, (size_t)npanels * HEAD_SYNC_INTS * sizeof(int), st.st);
+    auto head = [&](int64_t J, int64_t Jend, int64_t p) {
+        launch_potrf_head(A + J * TILE * (lda + 1), lda, (int)(Jend - J), w.inv + J * TILE * TILE,
+                          w.W + (p0 + p) * HEAD_PANEL * HEAD_PANEL, w.P, w.sync + (p0 + p) * HEAD_SYNC_INTS, has_sub, sub, info,
+                          (int)(J * TILE), pc);
+        cnt->launches += 1;
+    };
+    // pbuf rows [r0, r1) = A21[r0:r1, :] W^T
+    auto solve = [&](int64_t J, int64_t Jend, int64_t p, int64_t r0, int64_t r1, const LaunchCtx& c) {
+        if (r1 <= r0) return;
+        const int64_t rows = np - Jend * TILE;
+        GemmArgs g{};
+        g.C = w.pbuf[p & 1] + r0; g.ldc = rows;
+        g.A = A + Jend * TILE + r0 + J * TILE * lda; g.lda = lda;
+        g.B = w.W + (p0 + p) * HEAD_PANEL * HEAD_PANEL; g.ldb = HEAD_PANEL;
+        g.M = (int)(r1 - r0); g.N = (int)((Jend - J) * TILE); g.K = g.N;
+        g.alpha = 1.0; g.beta_one = 0; g.lower = 0; g.k_upto_col = 1;
+        cnt->launches += gemm_nt_launch(g, c) > 0;
+    };
+    // trailing matrix behind the panel (origin (Jend, Jend)) -= pbuf pbuf^T: the first `ntop` tile rows only (skip = 0,
+    // ntop > 0: the next panel's diagonal block) or everything but the first `skip` tile rows
+    auto update = [&](int64_t J, int64_t Jend, int64_t p, int64_t ntop, int64_t skip, const LaunchCtx& c) {
+        const int64_t rows = np - Jend * TILE;
+        GemmArgs g{};
+        g.C = A + Jend * TILE * (lda + 1); g.ldc = lda;
+        g.A = w.pbuf[p & 1]; g.lda = rows;
+        g.B = g.A; g.ldb = rows;
+        g.M = (int)(ntop > 0 ? ntop * TILE : rows); g.N = g.M; g.K = (int)((Jend - J) * TILE);
+        g.alpha = -1.0; g.beta_one = 1; g.lower = 1; g.row_skip = (int)skip;
+        cnt->launches += gemm_nt_launch(g, c) > 0;
+    };
+    auto copy_back = [&](int64_t J, int64_t Jend, int64_t p, cudaStream_t s) {
+        const int64_t rows = np - Jend * TILE;
+        cudaMemcpy2DAsync(A + Jend * TILE + J * TILE * lda, lda * sizeof(double), w.pbuf[p & 1], rows * sizeof(double),
+                          rows * sizeof(double), (size_t)((Jend - J) * TILE), cudaMemcpyDeviceToDevice, s);
+    };
+
+    int64_t J = jb_begin, Jend = std::min(J + PT, nb), p = 0;
+    if (!two) {
+        if (after_first_panel_may_start) (*after_first_panel_may_start)();
+        for (;; ++p) {
+            head(J, Jend, p);
+            const int64_t rows = np - Jend * TILE;
+            if (rows == 0) break;
+            solve(J, Jend, p, 0, rows, st);
+            update(J, Jend, p, 0, 0, st);
+            copy_back(J, Jend, p, st.st);
+            J = Jend;
+            Jend = std::min(J + PT, nb);
+        }
+        launch_transpose_tiles(w.inv + jb_begin * TILE * TILE, w.invT + jb_begin * TILE * TILE, nb - jb_begin, st.st);
+        cnt->launches += 1;
+        return p + 1;
+    }
+    cudaEventRecord(la->ev_trail, st.st);  // P starts after whatever precedes the factorisation on M (Gram of the first panel)
+    cudaStreamWaitEvent(la->panel, la->ev_trail, 0);
+    head(J, Jend, 0);
+    cudaEventRecord(la->ev_panel, la->panel);
+    if (after_first_panel_may_start) (*after_first_panel_may_start)();  // M: Gram columns behind the first panel, while P factors it
+    cudaEventRecord(la->ev_trail, st.st);
+    bool copies[2] = {false, false};
+    for (;; ++p) {
+        const int64_t rows = np - Jend * TILE;
+        if (rows == 0) break;
+        const int64_t Jend2 = std::min(Jend + PT, nb), nt2 = Jend2 - Jend;
+        const int64_t top = (rows <= SOLVE_SPLIT_ROWS) ? rows : nt2 * TILE;
+        cudaStreamWaitEvent(st.st, la->ev_panel, 0);      // M: head(p) done (W_p ready)
+        if (copies[p & 1]) {                              // pbuf[p & 1] has left for L (panel p-2)
+            cudaStreamWaitEvent(st.st, w.ev_copy[p & 1], 0);
+            cudaStreamWaitEvent(la->panel, w.ev_copy[p & 1], 0);
+        }
+        cudaStreamWaitEvent(la->panel, la->ev_trail, 0);  // P: the previous trailing update reached this panel's rows below
+        solve(J, Jend, p, 0, top, pc);
+        cudaEventRecord(w.ev_top, la->panel);
+        if (top < rows) {
+            solve(J, Jend, p, top, rows, st);
+            cudaEventRecord(w.ev_rest, st.st);
+        }
+        update(J, Jend, p, nt2, 0, pc);                   // the next panel's diagonal block ...
+        head(Jend, Jend2, p + 1);                         // ... and its head, while M applies panel p to everything else
+        cudaEventRecord(la->ev_panel, la->panel);
+        cudaStreamWaitEvent(st.st, w.ev_top, 0);
+        update(J, Jend, p, 0, nt2, st);
+        cudaEventRecord(la->ev_trail, st.st);
+        cudaStreamWaitEvent(sc.st, w.ev_top, 0);
+        if (top < rows) cudaStreamWaitEvent(sc.st, w.ev_rest, 0);
+        copy_back(J, Jend, p, sc.st);
+        cudaEventRecord(w.ev_copy[p & 1], sc.st);
+        copies[p & 1] = true;
+        J = Jend;
+        Jend = Jend2;
+    }
+    cudaStreamWaitEvent(st.st, la->ev_panel, 0);  // join: everything after the factorisation runs on M
+    for (int i = 0; i < 2; ++i)
+        if (copies[i]) cudaStreamWaitEvent(st.st, w.ev_copy[i], 0);
+    launch_transpose_tiles(w.inv + jb_begin * TILE * TILE, w.invT + jb_begin * TILE * TILE, nb - jb_begin, st.st);
+    cnt->launches += 1;
+    return p + 1;
+}
+
 }  // namespace fgp

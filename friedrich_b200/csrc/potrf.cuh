@@ -35,6 +35,20 @@ constexpr int DIAG_SMEM_BYTES = (128 * DIAG_DS + 96 * 33 + 128) * 8;
 // below n = 24576 and to rounding, ~1e-14 normwise, above.)
 inline int panel_tiles(int64_t np, int nranks = 1) { return (nranks == 1 && np >= 24576) ? 8 : 4; }
 
+// ---- panel head (potrf_head.cu) ------------------------------------------------------------------------------------
+constexpr int HEAD_PANEL = 512;   // columns of a panel = leading dimension of its inverse block W
+constexpr int HEAD_SYNC_INTS = 32;
+constexpr int HEAD_TIMEOUT = 0x7ffffff0;  // value of *info when a dependency wait inside the head kernel gave up  // counters one head launch uses (zeroed by the caller)
+cudaError_t potrf_head_prepare();
+int potrf_head_workers(int nt);     // worker CTAs of a head launch over nt block columns (grid = 1 + workers)
+// Factor the (128 nt)^2 diagonal block at A (ld = lda) in place and form its inverse: inv[nt][128*128] (the diagonal tiles'
+// inverses, zero upper triangle), W (512 x 512, ld 512: block (i, c), c <= i, of L11^-1), P = 512 x 512 scratch, sync =
+// HEAD_SYNC_INTS zeroed ints.  col_base: global column of A(0,0) for the failure report.  ONE launch on c.st.
+void launch_potrf_head(double* A, int64_t lda, int nt, double* inv, double* W, double* P, int* sync, int has_sub, double sub,
+                       int* info, int col_base, const LaunchCtx& c);
+// invT tiles = transposes of the nb inv tiles (the adjoint wavefront solve reads them); one launch
+void launch_transpose_tiles(const double* inv, double* invT, int64_t nb, cudaStream_t st);
+
 struct PotrfCounters {
     int64_t launches = 0;
 };
@@ -84,5 +98,28 @@ struct PotrfLookahead {
 void potrf_lower(double* A, int64_t lda, int64_t np, int64_t jb_begin, double* invdiag, double* invdiagT, int has_sub,
                  double sub, int* info, const LaunchCtx& st, const PotrfLookahead* la, PotrfCounters* cnt,
                  const std::function<void()>* after_first_panel_may_start = nullptr);
+
+// ---- the head schedule (default) -------------------------------------------------------------------------------------
+//   for each 512-column panel p = [J, Jend):
+//       L11, W = L11^-1                 potrf_head_kernel on the diagonal block            (panel stream; ONE launch)
+//       pbuf = A21 W^T                  gemm_nt, K <= 512, out of place (k_upto_col)        (top rows: panel stream; rest: main)
+//       A(next diagonal block) -= ..    gemm_nt lower on the first nt2 tile rows            (panel stream) -> next head
+//       A(everything else behind) -= pbuf pbuf^T     gemm_nt lower with row_skip           (main stream)
+//       L21 <- pbuf                     2-D copy                                            (side stream)
+// The chain between two heads is head -> solve of the next diagonal block's rows -> its update: three launches per 512
+// columns instead of twelve, none of which needs a whole SM; everything full-height trails on the main stream.
+struct PotrfWork {
+    double* inv;      // [nb][128*128] inverse diagonal tiles
+    double* invT;     // their transposes
+    double* W;        // [panels][512*512] inverse of every panel's diagonal block (ld 512)
+    double* P;        // 512*512 scratch of the head kernel
+    int* sync;        // [panels][HEAD_SYNC_INTS]
+    double* pbuf[2];  // >= (np - 128) * 512 doubles each: the solved panel below its diagonal block, ld = rows below
+    cudaEvent_t ev_top, ev_rest, ev_copy[2];
+};
+// `p0`: slot of the first panel's W / sync (panels are [jb_begin + 4 i, ..)); returns the number of panels factored.
+int64_t potrf_lower_head(double* A, int64_t lda, int64_t np, int64_t jb_begin, const PotrfWork& w, int64_t p0, int has_sub,
+                         double sub, int* info, const LaunchCtx& st, const PotrfLookahead* la, PotrfCounters* cnt,
+                         const std::function<void()>* after_first_panel_may_start = nullptr);
 
 }  // namespace fgp

@@ -115,7 +115,11 @@ int fgp_download_alpha(fgp_model* m, double* alpha);
  *                      is ignored, NaN allowed) become resident WITHOUT refitting; the inverse diagonal blocks, alpha and
  *                      L^-1 y that the device path caches are rebuilt from L.  The handle then behaves as after fgp_fit.
  * fgp_inverse_columns  selected columns of K^-1 (`covmat_cholesky.inverse()`, optimizer.rs:32, :169) as left on the device
- *                      by the last fgp_lml_gradient call; out is n x ncols, ld = ldo.  Diagnostics / tests. */
+ *                      by the last fgp_lml_gradient call; out is n x ncols, ld = ldo.  Diagnostics / tests.
+ * fgp_factor_digest    three deterministic sums over the lower triangle of the resident factor (sum, sum of squares,
+ *                      position-weighted sum): bitwise-equal factors give bitwise-equal digests, so ranks of a sharded fit
+ *                      (and a sharded against a single-GPU fit) can be compared without moving 8 n^2 bytes. out[3]. */
+int fgp_factor_digest(fgp_model* m, double* out);
 int fgp_upload_state(fgp_model* m, const double* X, int64_t ldx, int64_t n, int64_t d, const double* y_resid,
                      const double* L, int64_t ldl);
 int fgp_inverse_columns(fgp_model* m, const int64_t* cols, int64_t ncols, double* out, int64_t ldo);
@@ -160,7 +164,10 @@ int fgp_set_profiling(fgp_model* m, int on);
 /* Scheduling knobs (results are identical either way; used by bench.py / tests for A-B runs).
  * FGP_OPT_LOOKAHEAD (default 1): factor the next panel on a second, high-priority stream while the trailing update
  * of the current one runs. */
-enum fgp_option { FGP_OPT_LOOKAHEAD = 1 };
+/* FGP_OPT_HEAD (default 1): factor each 512-column panel's diagonal block and its inverse in ONE multi-CTA launch
+ * (csrc/potrf_head.cu) and solve everything below it as one K <= 512 GEMM; 0 = the per-block-column schedule
+ * (diagonal tile / panel solve / rank-128 update launch triples). Results agree to rounding, not bit for bit. */
+enum fgp_option { FGP_OPT_LOOKAHEAD = 1, FGP_OPT_HEAD = 2 };
 int fgp_set_option(fgp_model* m, int option, int64_t value);
 int fgp_profile_summary(const fgp_model* m, double* ms, double* flops, int64_t* count);
 /* Resident-input predict for kernel-only timing: stage queries once, then run the device part repeatedly. */
@@ -176,10 +183,15 @@ void fgp_free_pinned(void* p);
 int fgp_dbg_gemm_nt(int device, double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb,
                     int M, int N, int K, double alpha, int beta_one, int lower);
 
-/* measurement hook: `reps` back-to-back launches of the production GEMM kernel on device-resident zero matrices, SYRK-shaped
+/* measurement hook: `reps` back-to-back launches of the production GEMM kernel on device-resident random matrices, SYRK-shaped
  * (C (M x N) -= A A[:N]^T, A is M x K; lower != 0: only tiles on/below the diagonal). *ms_out = CUDA-event time per launch,
  * *flops_out = algorithmic flops per launch. Used by tools/gemm_bench.py for the kernel's isolated roofline figure. */
 int fgp_dbg_gemm_bench(int device, int M, int N, int K, int lower, int beta_one, int reps, double* ms_out, double* flops_out);
+
+/* test hook: the panel head kernel (csrc/potrf_head.cu) alone: A is (128 nt)^2 column-major SPD, nt = 1..4 -> L in its lower
+ * triangle; W (same shape, ld = 128 nt) <- L^-1; *info_out = 0, the 1-based failing column, or the kernel's time-out code */
+int fgp_dbg_potrf_head(int device, double* A, int nt, double* W, int has_sub, double sub, int* info_out, int reps,
+                       double* ms_out); /* reps > 0 and ms_out != NULL: also the kernel's CUDA-event time on fresh copies of A */
 
 /* test hook, host only: the branch-free exp(x), x <= 0, that the device kernels evaluate (csrc/kernel_eval.cuh exp_nonpos) */
 double fgp_dbg_exp(double x);
@@ -195,6 +207,9 @@ int fgp_dbg_gemm_occupancy32(int device); /* the 32-row shape used for sub-wave 
 /* test hook, host only: the (tile row, tile column) each thread block of a lower-mode GEMM launch computes, for M x N
  * extents and tile-column groups of `grp` columns `stride` apart (the sharded trailing update); returns the tile count. */
 int64_t fgp_dbg_lower_tiles(int M, int N, int grp, int stride, int* ti_out, int* tj_out, int64_t capacity);
+/* the same with the first `row_skip` tile rows left out (the trailing update behind a panel whose successor's diagonal
+ * block is updated by its own launch on the panel stream) */
+int64_t fgp_dbg_lower_tiles_skip(int M, int N, int grp, int stride, int row_skip, int* ti_out, int* tj_out, int64_t capacity);
 
 #ifdef __cplusplus
 }

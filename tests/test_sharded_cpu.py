@@ -94,3 +94,23 @@ def test_lower_mode_block_to_tile_map_is_exact(tm, tn, grp, stride):
         R *= 2
     bands = [t[0] // R for t in got]
     assert bands == sorted(bands)
+
+
+@pytest.mark.parametrize("tm,tn,grp,stride,skip", [(7, 7, 1, 1, 4), (9, 4, 1, 1, 4), (128, 128, 1, 1, 4), (20, 8, 4, 4, 4),
+                                                   (61, 15, 4, 16, 4), (250, 32, 4, 32, 4), (33, 33, 1, 1, 3), (5, 5, 1, 1, 5),
+                                                   (256, 256, 1, 1, 4), (1100, 40, 4, 32, 2)])
+def test_lower_mode_tile_map_with_skipped_top_rows(tm, tn, grp, stride, skip):
+    """The trailing update behind a panel leaves out the next panel's diagonal block (updated by its own, earlier launch on
+    the panel stream): the first `skip` tile rows are not visited, everything else exactly once."""
+    import ctypes as C
+    from friedrich_b200 import _native as N
+    expect = []
+    for jl in range(tn):
+        tj = (jl // grp) * stride + jl % grp
+        expect += [(ti, tj) for ti in range(max(tj, skip), tm)]
+    cap = len(expect) + 8
+    ti, tj = (C.c_int * cap)(), (C.c_int * cap)()
+    tiles = N.lib().fgp_dbg_lower_tiles_skip(tm * 128, tn * 128, grp, stride, skip, ti, tj, cap)
+    assert tiles == len(expect)
+    got = [(ti[b], tj[b]) for b in range(tiles)]
+    assert sorted(got) == sorted(expect)
