@@ -339,6 +339,8 @@ void comm_release(fgp_model* m) {
     if (c->ev_bcast) cudaEventDestroy(c->ev_bcast);
     for (cudaEvent_t e : c->ev_trail)
         if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_copy)
+        if (e) cudaEventDestroy(e);
     delete c;
     m->comm = nullptr;
 }
@@ -987,7 +989,9 @@ FGP_EXPORT int fgp_comm_init_rank(fgp_model* m, const void* id, size_t bytes, in
         cudaEventCreateWithFlags(&c->ev_col, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_bcast, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_trail[0], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_trail[1], cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&c->ev_trail[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_copy[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_copy[1], cudaEventDisableTiming) != cudaSuccess) {
         comm_release(m);
         return fail(m, FGP_ERR_CUDA, "event creation failed");
     }
@@ -1045,6 +1049,14 @@ FGP_EXPORT int fgp_shard_plan(int64_t n, int nranks, int rank, int64_t* panel_co
 }
 
 namespace {
+int run_factor_sharded(fgp_model* m, const fgp_kernel_desc* kernel, const KernelTraits& kt, double noise, int has_eps, double eps) {
+    if (!m->head_schedule) return factor_sharded(m, kernel, kt, noise, has_eps, eps);
+    PotrfWork w;
+    int64_t p0 = 0;
+    FGP_TRY(prepare_head_work(m, 0, &w, &p0));
+    return factor_sharded_head(m, kernel, kt, noise, has_eps, eps, w);
+}
+
 int finish_sharded(fgp_model* m, int rc) {
     if (rc != FGP_OK) return rc;
     CU(m, cudaMemcpyAsync(m->info_h, m->info_d, sizeof(int), cudaMemcpyDeviceToHost, m->st));
@@ -1117,7 +1129,7 @@ FGP_EXPORT int fgp_fit_sharded(fgp_model* m, const double* X, int64_t ldx, int64
             return fail(m, FGP_ERR_COMM, "ncclBroadcast of the training set failed");
     }
     FGP_TRY(convert_staged_inputs(m));
-    int rc = finish_sharded(m, factor_sharded(m, kernel, kt, noise, has_eps, eps));
+    int rc = finish_sharded(m, run_factor_sharded(m, kernel, kt, noise, has_eps, eps));
     int rc2 = end_timed(m);
     return rc != FGP_OK ? rc : rc2;
 }
@@ -1136,7 +1148,7 @@ FGP_EXPORT int fgp_refit_sharded(fgp_model* m, const fgp_kernel_desc* kernel, do
         return reserve_sharded(m);
     };
     FGP_TRY(comm_agree(m, local()));
-    int rc = finish_sharded(m, factor_sharded(m, kernel, kt, noise, has_eps, eps));
+    int rc = finish_sharded(m, run_factor_sharded(m, kernel, kt, noise, has_eps, eps));
     int rc2 = end_timed(m);
     return rc != FGP_OK ? rc : rc2;
 }

@@ -303,13 +303,13 @@ __device__ __noinline__ void head_x32(double* T, double* Wx, const double* rdiag
 
 // (b) rows below the pivot block: A_below <- A_below X^T with X = L_pp^-1 (already in place of L_pp), on the tensor pipe.
 // Unit = 8 rows x 32 columns (all of the unit's A fragments are read before anything is written: in place is safe);
-// X(n, k) = 0 for k > n, so tile column ni contracts over k < 8 (ni + 1).
-__device__ __noinline__ void head_rows_below_mma(double* T, int s, int warp, int lane) {
+// X(n, k) = 0 for k > n, so tile column ni contracts over k < 8 (ni + 1).  Units [u_begin, u_end) are shared by the nw warps
+// of the calling group (gw = index inside it); unit u covers band rows 32 + 8 u ..: units 0..3 are the NEXT pivot block's rows.
+__device__ __noinline__ void head_rows_below_mma(double* T, int s, int u_begin, int u_end, int gw, int nw, int lane) {
     const int S = ht_stride(s);
     double* Tb = T + ht_base(s);
     const int g = lane >> 2, t = lane & 3;
-    const int units = (96 - 32 * s) / 8;
-    for (int u = warp; u < units; u += 8) {
+    for (int u = u_begin + gw; u < u_end; u += nw) {
         const int m0 = 32 + 8 * u;
         double fa[8], acc[4][2];
 #pragma unroll
@@ -330,42 +330,45 @@ __device__ __noinline__ void head_rows_below_mma(double* T, int s, int warp, int
     }
 }
 
-// (c) in-tile SYRK on the tensor pipe: A22 -= X X^T, X = rows below of sub-panel s.  Unit = 32 rows x 16 columns of a
-// 32-block (bi, bj <= bi); warp w takes units w, w + 8, ...
-__device__ __noinline__ void head_syrk(double* T, int s, int warp, int lane) {
-    const int nbk = 3 - s;
-    const int units = nbk * (nbk + 1);  // lower blocks x 2 column halves
+// (c) in-tile SYRK on the tensor pipe: A22 -= X X^T, X = rows below of sub-panel s.  Unit q = 16 rows x 16 columns of the
+// 32-block blk = q / 4 (blocks (bi, bj <= bi) of the trailing part, enumerated row by row: block 0 is the NEXT pivot block),
+// quarter (hr, hf) = (row half, column half); the strictly upper quarter of a diagonal block is skipped, and so are its 8 x 8
+// tiles above the diagonal.  Units [q_begin, q_end) are shared by the nw warps of the calling group.
+__device__ __noinline__ void head_syrk(double* T, int s, int q_begin, int q_end, int gw, int nw, int lane) {
     const int S = ht_stride(s);
     const double* Tb = T + ht_base(s);
     const int g = lane >> 2, t = lane & 3;
-    for (int u = warp; u < units; u += 8) {
-        const int blk = u >> 1, hf = u & 1;
+    for (int q = q_begin + gw; q < q_end; q += nw) {
+        const int blk = q >> 2, hr = (q >> 1) & 1, hf = q & 1;
         int bi = 0, rem = blk;
         while (rem > bi) { rem -= bi + 1; ++bi; }  // blk = bi (bi + 1) / 2 + bj
         const int bj = rem;
-        const int m0 = 32 + 32 * bi, n0 = 32 + 32 * bj + 16 * hf;  // band-relative rows of the two operands
-        double acc[4][2][2];
+        const bool dg = (bi == bj);
+        if (dg && hr == 0 && hf == 1) continue;
+        const int m0 = 32 + 32 * bi + 16 * hr, n0 = 32 + 32 * bj + 16 * hf;  // band-relative rows of the two operands
+        double acc[2][2][2];
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        const bool skip01 = dg && hr == hf;  // diagonal quarter: tile (mi = 0, ni = 1) lies above the diagonal
 #pragma unroll
         for (int kk = 0; kk < 32; kk += 4) {
-            double fa[4], fb[2];
+            double fa[2], fb[2];
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) fa[mi] = Tb[(kk + t) * S + m0 + 8 * mi + g];
+            for (int mi = 0; mi < 2; ++mi) fa[mi] = Tb[(kk + t) * S + m0 + 8 * mi + g];
 #pragma unroll
             for (int ni = 0; ni < 2; ++ni) fb[ni] = Tb[(kk + t) * S + n0 + 8 * ni + g];
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 2; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], fa[mi], fb[ni]);
+            dmma884(acc[0][0][0], acc[0][0][1], fa[0], fb[0]);
+            if (!skip01) dmma884(acc[0][1][0], acc[0][1][1], fa[0], fb[1]);
+            dmma884(acc[1][0][0], acc[1][0][1], fa[1], fb[0]);
+            dmma884(acc[1][1][0], acc[1][1][1], fa[1], fb[1]);
         }
         // C(row, col): tile row 32 s + m0 + .., tile column 32 s + n0 + .. = band s + 1 + bj
         const int bc = s + 1 + bj, Sc = ht_stride(bc);
-        double* Tc = T + ht_base(bc) + 32 * (bi - bj);
+        double* Tc = T + ht_base(bc) + 32 * (bi - bj) + 16 * hr;
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 2; ++ni)
 #pragma unroll
@@ -488,46 +491,53 @@ __device__ void head_diag_tile(double* smem, uint64_t* bar, uint32_t parity, dou
     mbar_wait(bar, parity);
     HEAD_MARK(1);
     const int sub_ok = has_sub && sub > 0.0;
-    const int gw = (warp < 4) ? warp - 1 : warp - 2;  // index of warps 1,2,3,5,6,7 in the inverse group (warps 0 and 4: unused)
-    const bool inv_group = (warp != 0 && warp != 4);
+    const int gw = (warp < 4) ? warp - 1 : warp - 2;  // index of warps 1,2,3,5,6,7 in the trailing group (warps 0 and 4: not in it)
+    const bool grp = (warp != 0 && warp != 4);
+    // pivot block s by warp 0: factor, store to global memory (zeros above the diagonal included) before the inverse replaces it
+    auto pivot_and_invert = [&](int s) {
+        head_pivot32(T, rdiag, s, lane, sub_ok, sub, info, col_base);
+        HEAD_MARK(2 + 6 * s);
+        const double* Tb = T + ht_base(s);
+        const int S = ht_stride(s);
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 8) {
+            double v[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[c] = Tb[(c0 + c) * S + lane];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) Ag[32 * s + lane + (int64_t)(32 * s + c0 + c) * lda] = v[c];
+        }
+        __syncwarp();
+        head_x32(T, Wx, rdiag, s, lane);
+        HEAD_MARK(3 + 6 * s);
+    };
+    if (warp == 0) pivot_and_invert(0);
+    __syncthreads();
+    // In-tile look-ahead: after sub-panel s only what the NEXT pivot block needs is done by everybody (A: its 32 rows of the
+    // rows-below solve, B: its own SYRK block); then warp 0 runs the next pivot chain while the trailing group finishes
+    // sub-panel s (the other rows below, the other SYRK blocks) and advances the tile's inverse.
 #pragma unroll 1
-    for (int s = 0; s < 4; ++s) {
+    for (int s = 0; s < 3; ++s) {
+        const int nu = (96 - 32 * s) / 8, nbk = 3 - s, nq = 2 * nbk * (nbk + 1);
+        HEAD_MARK(4 + 6 * s);
+        if (warp < 4) head_rows_below_mma(T, s, 0, 4, warp, 4, lane);             // A
+        __syncthreads();
+        HEAD_MARK(5 + 6 * s);
+        if (warp < 4) head_syrk(T, s, 0, 4, warp, 4, lane);                       // B
+        __syncthreads();
+        HEAD_MARK(6 + 6 * s);
         if (warp == 0) {
-            head_pivot32(T, rdiag, s, lane, sub_ok, sub, info, col_base);
-            HEAD_MARK(2 + 6 * s);
-            // the factored pivot block goes to global memory before its inverse replaces it (zeros above the diagonal included)
-            const double* Tb = T + ht_base(s);
-            const int S = ht_stride(s);
-#pragma unroll
-            for (int c0 = 0; c0 < 32; c0 += 8) {
-                double v[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) v[c] = Tb[(c0 + c) * S + lane];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) Ag[32 * s + lane + (int64_t)(32 * s + c0 + c) * lda] = v[c];
-            }
-            __syncwarp();
-            head_x32(T, Wx, rdiag, s, lane);
-            HEAD_MARK(3 + 6 * s);
-        } else if (inv_group && s > 0) {
-            head_inverse_apply(T, Ws, s - 1, gw, 6, lane);  // S_{s-1,j} was formed at the end of the previous round
+            pivot_and_invert(s + 1);                                              // C, warp 0
+        } else if (grp) {                                                         // C, trailing group
+            head_rows_below_mma(T, s, 4, nu, gw, 6, lane);
             head_group_bar(1, 192);
-            // the sums of the NEXT row block need nothing from the pivot block being factored right now: L_sk (k < s) is final
-            // and so is every X_kj with k < s
-            head_inverse_sums(T, Ws, s, gw, 6, lane, Ag, lda);
-            HEAD_MARK(3 + 6 * s);
+            head_syrk(T, s, 4, nq, gw, 6, lane);
+            head_inverse_apply(T, Ws, s, gw, 6, lane);   // S_sj was formed one round earlier (no-op for s = 0)
+            head_group_bar(1, 192);
+            head_inverse_sums(T, Ws, s + 1, gw, 6, lane, Ag, lda);  // L_{s+1,k} and X_kj, k <= s, are final
+            HEAD_MARK(7 + 6 * s);
         }
         __syncthreads();
-        if (s < 3) {
-            HEAD_MARK(4 + 6 * s);
-            head_rows_below_mma(T, s, warp, lane);
-            HEAD_MARK(5 + 6 * s);
-            __syncthreads();
-            HEAD_MARK(6 + 6 * s);
-            head_syrk(T, s, warp, lane);
-            HEAD_MARK(7 + 6 * s);
-            __syncthreads();
-        }
     }
     HEAD_MARK(26);
     head_inverse_apply(T, Ws, 3, warp, 8, lane);  // S_3j is ready: only the last row block's products are exposed

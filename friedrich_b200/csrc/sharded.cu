@@ -201,4 +201,165 @@ int factor_sharded(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& 
     return FGP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same distribution on the HEAD schedule (potrf.cuh): per panel p the owner runs, on its panel stream,
+//     diagonal block of p  -= (rows of p in panel p-1) (..)^T          gemm_nt lower, from the previous panel buffer
+//     L11, W = L11^-1                                                   potrf_head_kernel (one launch)
+//     rows below in p's columns -= (panel p-1 rows below)(rows of p)^T  gemm_nt, on the side stream beside the head
+//     buffer rows below = A21 W^T                                       gemm_nt, K <= 512, out of place
+//     buffer top = L11                                                  2-D copy
+// then the whole panel buffer is broadcast; every rank applies it to the panels it owns behind p+1 in one launch on the main
+// stream (panel p+1 is its owner's look-ahead above) and keeps a copy of the panel in its L.  The arithmetic per tile is
+// that of the single-GPU head schedule, so the factors are bit-identical.
+int factor_sharded_head(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& kt, double noise, int has_eps, double eps,
+                        const PotrfWork& w) {
+    fgp_comm* cm = m->comm;
+    const int P = cm->nranks, r = cm->rank;
+    const NcclApi* nccl = nccl_api();
+    if (P > 1 && !nccl) return fail(m, FGP_ERR_COMM, "libnccl.so.2 could not be loaded");
+    const int64_t np = m->np, nb = np / TILE, PT = HEAD_PANEL / TILE, NP = (nb + PT - 1) / PT;
+    FGP_TRY(reserve_sharded(m));
+    CU(m, cudaMemsetAsync(m->info_d, 0, sizeof(int), m->st));
+    CU(m, cudaMemsetAsync(w.sync, 0, (size_t)NP * HEAD_SYNC_INTS * sizeof(int), m->st));
+    cm->bcast_bytes = 0.0;
+    for (int64_t p = r; p < NP; p += P) {  // Gram: only the block columns this rank owns (algebra/mod.rs:67-79 restricted to them)
+        const int64_t J = p * PT, Jend = std::min<int64_t>(J + PT, nb);
+        PairArgs pa{};
+        pa.xa_c = pa.xb_c = m->xc.p;
+        pa.xa_r = pa.xb_r = m->xr.p;
+        pa.na = pa.nb = m->nc.p;
+        pa.dp = (int)m->dp;
+        pa.rows = pa.cols = np;
+        pa.row_tile0 = (int)J;
+        pa.col_tile0 = (int)(J * TILE / PAIR_TN);
+        pa.col_tiles = (int)((Jend - J) * TILE / PAIR_TN);
+        pa.symmetric = 1;
+        write_covariance(m, kt, kd, pa, m->L.p, m->cap, m->n, m->n, noise * noise);
+    }
+    const LaunchCtx mc = m->ctx();
+    LaunchCtx pc = mc, sc = mc;
+    pc.st = m->st2;
+    sc.st = m->st3;
+    PotrfCounters cnt;
+    CU(m, cudaEventRecord(m->evA, m->st));
+    CU(m, cudaStreamWaitEvent(m->st2, m->evA, 0));
+    auto gemm = [&](double* Cp, int64_t ldc, const double* Ap, int64_t lda, const double* Bp, int64_t ldb, int64_t M, int64_t N,
+                    int64_t K, double alpha, int beta_one, int lower, int k_upto, const LaunchCtx& c) {
+        GemmArgs g{};
+        g.C = Cp; g.ldc = ldc;
+        g.A = Ap; g.lda = lda;
+        g.B = Bp; g.ldb = ldb;
+        g.M = (int)M; g.N = (int)N; g.K = (int)K;
+        g.alpha = alpha; g.beta_one = beta_one; g.lower = lower; g.k_upto_col = k_upto;
+        cnt.launches += gemm_nt_launch(g, c) > 0;
+    };
+    bool copy_pending[2] = {false, false};
+    for (int64_t p = 0; p < NP; ++p) {
+        const int64_t J = p * PT, Jend = std::min<int64_t>(J + PT, nb);
+        const int64_t rows = np - J * TILE, wc = (Jend - J) * TILE, below = rows - wc;
+        const int owner = shard_owner(p, P);
+        double* buf = cm->pbuf[p & 1].p;
+        if (p >= 2) {  // the trailing update with panel p-2 has left this buffer and reached this panel's columns
+            CU(m, cudaStreamWaitEvent(m->st2, cm->ev_trail[p & 1], 0));
+            CU(m, cudaStreamWaitEvent(cm->st_comm, cm->ev_trail[p & 1], 0));
+            if (copy_pending[p & 1]) {  // ... and so has this rank's copy of it into L
+                CU(m, cudaStreamWaitEvent(m->st2, cm->ev_copy[p & 1], 0));
+                CU(m, cudaStreamWaitEvent(cm->st_comm, cm->ev_copy[p & 1], 0));
+            }
+        }
+        if (owner == r) {
+            double* Ajj = m->L.p + J * TILE * (m->cap + 1);
+            double* A21 = m->L.p + Jend * TILE + J * TILE * m->cap;
+            if (p >= 1) {  // look-ahead: this panel's columns get the previous panel's update here, not in the main-stream launch
+                const int64_t Jp = (p - 1) * PT, rows_p = np - Jp * TILE, wp = (J - Jp) * TILE;
+                const double* prev = cm->pbuf[(p - 1) & 1].p;
+                const double* mine = prev + (J - Jp) * TILE;  // rows of this panel's diagonal block inside the previous buffer
+                gemm(Ajj, m->cap, mine, rows_p, mine, rows_p, wc, wc, wp, -1.0, 1, 1, 0, pc);
+                if (below > 0) {
+                    CU(m, cudaEventRecord(m->evC, m->st2));
+                    CU(m, cudaStreamWaitEvent(m->st3, m->evC, 0));
+                    gemm(A21, m->cap, prev + (Jend - Jp) * TILE, rows_p, mine, rows_p, below, wc, wp, -1.0, 1, 0, 0, sc);
+                    CU(m, cudaEventRecord(m->evC, m->st3));
+                }
+            }
+            launch_potrf_head(Ajj, m->cap, (int)(Jend - J), w.inv + J * TILE * TILE, w.W + p * HEAD_PANEL * HEAD_PANEL, w.P,
+                              w.sync + p * HEAD_SYNC_INTS, has_eps, eps, m->info_d, (int)(J * TILE), pc);
+            cnt.launches += 1;
+            CU(m, cudaMemcpy2DAsync(buf, rows * sizeof(double), Ajj, m->cap * sizeof(double), wc * sizeof(double), (size_t)wc,
+                                    cudaMemcpyDeviceToDevice, m->st2));
+            if (below > 0) {
+                if (p >= 1) CU(m, cudaStreamWaitEvent(m->st2, m->evC, 0));
+                gemm(buf + wc, rows, A21, m->cap, w.W + p * HEAD_PANEL * HEAD_PANEL, HEAD_PANEL, below, wc, wc, 1.0, 0, 0, 1, pc);
+            }
+            CU(m, cudaEventRecord(cm->ev_col, m->st2));
+            CU(m, cudaStreamWaitEvent(cm->st_comm, cm->ev_col, 0));
+            if (below > 0) {  // L21 <- buffer, off the critical path (nothing reads these columns of L before the fit ends)
+                CU(m, cudaStreamWaitEvent(m->st3, cm->ev_col, 0));
+                CU(m, cudaMemcpy2DAsync(A21, m->cap * sizeof(double), buf + wc, rows * sizeof(double), below * sizeof(double),
+                                        (size_t)wc, cudaMemcpyDeviceToDevice, m->st3));
+                CU(m, cudaEventRecord(cm->ev_copy[p & 1], m->st3));
+                copy_pending[p & 1] = true;
+            }
+        }
+        if (P > 1) {
+            // profiled (class "other") only on the owner: there the duration is the send itself, elsewhere it includes the wait
+            // for the owner's factorisation; the "flops" slot carries the bytes
+            LaunchCtx bc = mc;
+            bc.st = cm->st_comm;
+            if (owner != r) bc.prof = nullptr;
+            ProfScope ps(bc, PROF_OTHER, (double)rows * wc * sizeof(double));
+            NC(m, nccl->Broadcast(buf, buf, (size_t)rows * wc, ncclDouble, owner, cm->comm, cm->st_comm));
+            cm->bcast_bytes += (double)rows * wc * sizeof(double);
+        }
+        CU(m, cudaEventRecord(cm->ev_bcast, cm->st_comm));
+        CU(m, cudaStreamWaitEvent(m->st2, cm->ev_bcast, 0));  // the next owner's look-ahead reads the buffer on st2 / st3
+        CU(m, cudaStreamWaitEvent(m->st, cm->ev_bcast, 0));
+        {
+            // every owned panel c > p, c != p+1, in ONE launch: the owned panels are groups of PT tile columns, P*PT apart
+            int64_t c_first = p + 1 + ((r - (p + 1)) % P + P) % P;
+            if (c_first == p + 1) c_first += P;
+            if (c_first < NP) {
+                const int64_t c0 = c_first * PT;
+                int64_t ncols = 0;
+                for (int64_t c = c_first; c < NP; c += P) ncols += std::min<int64_t>(PT, nb - c * PT);
+                GemmArgs g{};
+                g.C = m->L.p + c0 * TILE + c0 * TILE * m->cap; g.ldc = m->cap;
+                g.A = buf + (c0 - J) * TILE; g.lda = rows;
+                g.B = g.A; g.ldb = rows;
+                g.M = (int)(np - c0 * TILE); g.N = (int)(ncols * TILE); g.K = (int)wc;
+                g.alpha = -1.0; g.beta_one = 1; g.lower = 1;
+                g.grp = (int)PT; g.stride = (int)(P * PT);
+                cnt.launches += gemm_nt_launch(g, mc) > 0;
+            }
+        }
+        if (owner != r)
+            CU(m, cudaMemcpy2DAsync(m->L.p + J * TILE + J * TILE * m->cap, m->cap * sizeof(double), buf, rows * sizeof(double),
+                                    rows * sizeof(double), (size_t)wc, cudaMemcpyDeviceToDevice, m->st));
+        CU(m, cudaEventRecord(cm->ev_trail[p & 1], m->st));
+    }
+    // join the panel and side streams; the inverted diagonal tiles live with their owners and every rank needs them for the solves
+    CU(m, cudaEventRecord(cm->ev_col, m->st2));
+    CU(m, cudaStreamWaitEvent(m->st, cm->ev_col, 0));
+    for (int i = 0; i < 2; ++i)
+        if (copy_pending[i]) CU(m, cudaStreamWaitEvent(m->st, cm->ev_copy[i], 0));
+    if (P > 1) {
+        CU(m, cudaStreamWaitEvent(m->st2, cm->ev_trail[(NP - 1) & 1], 0));
+        NC(m, nccl->GroupStart());
+        for (int64_t p = 0; p < NP; ++p) {
+            const int64_t J = p * PT, Jend = std::min<int64_t>(J + PT, nb);
+            NC(m, nccl->Broadcast(m->inv.p + J * TILE * TILE, m->inv.p + J * TILE * TILE, (size_t)(Jend - J) * TILE * TILE, ncclDouble,
+                                shard_owner(p, P), cm->comm, m->st2));
+        }
+        NC(m, nccl->GroupEnd());
+        info_encode_kernel<<<1, 1, 0, m->st2>>>(m->info_d, 0);
+        NC(m, nccl->AllReduce(m->info_d, m->info_d, 1, ncclInt, ncclMin, cm->comm, m->st2));  // first failing column anywhere
+        info_encode_kernel<<<1, 1, 0, m->st2>>>(m->info_d, 1);
+        CU(m, cudaEventRecord(cm->ev_bcast, m->st2));
+        CU(m, cudaStreamWaitEvent(m->st, cm->ev_bcast, 0));
+    }
+    launch_transpose_tiles(m->inv.p, m->invT.p, nb, m->st);
+    m->launches += cnt.launches + 1;
+    return FGP_OK;
+}
+
 }  // namespace fgp

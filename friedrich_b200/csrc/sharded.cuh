@@ -17,6 +17,7 @@ struct fgp_comm {
     cudaEvent_t ev_col = nullptr;            // a block column of the panel is final (recorded on the panel stream)
     cudaEvent_t ev_bcast = nullptr;          // panel J has arrived (recorded on the comm stream)
     cudaEvent_t ev_trail[2] = {nullptr, nullptr};  // trailing update with panel J done (main stream), index J & 1
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};   // this rank's copy of panel buffer J & 1 back into L done (side stream)
     double bcast_bytes = 0.0;                // bytes this rank sent or received in the last sharded factorisation
 };
 
@@ -30,5 +31,8 @@ int reserve_sharded(fgp_model* m);
 
 // Gram assembly of the owned panels + the sharded factorisation; on return every rank holds the complete factor in m->L.
 int factor_sharded(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& kt, double noise, int has_eps, double eps);
+// the same on the head schedule (one potrf_head_kernel per panel; bit-identical to the single-GPU head schedule)
+int factor_sharded_head(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& kt, double noise, int has_eps, double eps,
+                        const PotrfWork& w);
 
 }  // namespace fgp

@@ -37,8 +37,8 @@ int main(int argc, char** argv) {
         static char buf[32][24];
         for (int s = 0; s < 4; ++s) {
             snprintf(buf[2 + 6 * s], 24, "piv%d", s); snprintf(buf[3 + 6 * s], 24, "x32/inv%d", s);
-            snprintf(buf[4 + 6 * s], 24, "bar%da", s); snprintf(buf[5 + 6 * s], 24, "below%d", s);
-            snprintf(buf[6 + 6 * s], 24, "bar%db", s); snprintf(buf[7 + 6 * s], 24, "syrk%d", s);
+            snprintf(buf[4 + 6 * s], 24, "A%d start", s); snprintf(buf[5 + 6 * s], 24, "B%d start", s);
+            snprintf(buf[6 + 6 * s], 24, "C%d start", s); snprintf(buf[7 + 6 * s], 24, "grp%d done", s);
             for (int k = 2; k < 8; ++k) names[k + 6 * s] = buf[k + 6 * s];
         }
         names[26] = "loop_end"; names[27] = "apply3"; names[28] = "stored";
