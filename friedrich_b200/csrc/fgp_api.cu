@@ -76,6 +76,7 @@ void solve_alpha(fgp_model* m) {
 // (fgp_upload_state) needs none: the panel table is simply emptied.
 int rebuild_panel_inverses(fgp_model* m) {
     m->pstart.clear();
+    m->w_valid = false;
     return FGP_OK;
 }
 
@@ -149,9 +150,12 @@ int factor_resident(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits&
         FGP_TRY(prepare_head_work(m, 0, &w, &p0));
         potrf_lower_head(m->L.p, m->cap, m->np, 0, w, p0, has_eps, eps, m->info_d, m->ctx(), m->lookahead ? &la : nullptr, &cnt,
                          &rest);
+        m->w_valid = true;
     } else {
         potrf_lower(m->L.p, m->cap, m->np, 0, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->ctx(),
                     m->lookahead ? &la : nullptr, &cnt, &rest);
+        m->pstart.clear();
+        m->w_valid = false;
     }
     m->launches += cnt.launches;
     CU(m, cudaMemcpyAsync(m->info_h, m->info_d, sizeof(int), cudaMemcpyDeviceToHost, m->st));
@@ -277,7 +281,11 @@ int predict_device(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& 
         m->have_mean = true;
     }
     if (want_var) {
-        if (m->lookahead)
+        if (m->w_valid && !m->pstart.empty() && qp <= m->cap)  // panels of the head schedule: two K <= 512 launches per 512 columns
+            m->launches += trsm_fwd_t_panels(m->bt.p, qp, qp, m->L.p, m->cap, m->Wp.p, m->pstart.data(), (int64_t)m->pstart.size(),
+                                             np / TILE, np / TILE, m->pbuf[0].p, m->pbuf[1].p, m->ctx(),
+                                             m->lookahead ? m->st2 : nullptr, m->evA, m->evB, m->evC);
+        else if (m->lookahead)
             m->launches += trsm_fwd_t_lookahead(m->bt.p, qp, qp, m->L.p, m->cap, m->inv.p, np / TILE, m->ctx(), m->st2, m->evA,
                                                 m->evB);
         else
@@ -884,18 +892,28 @@ FGP_EXPORT int fgp_add_samples(fgp_model* m, const double* Xnew, int64_t ldx, in
     write_covariance(m, kt, kernel, pa, m->L.p, m->cap, n_new, n_new, noise * noise);
     // rows [jb*128, np_new) x columns [0, jb*128):  A <- A * L11^-T, and the trailing block gets -= A A^T
     double* Arows = m->L.p + jb * TILE;  // row offset inside every column
-    m->launches += trsm_fwd_t(Arows, m->cap, np_new - jb * TILE, m->L.p, m->cap, m->inv.p, 0, jb, Arows + jb * TILE * m->cap,
-                              m->ctx());
     PotrfCounters cnt;
     const PotrfLookahead la{m->st2, m->evA, m->evB, m->st3, m->evC, m->evD};
+    const int64_t Mrows = np_new - jb * TILE;
     if (m->head_schedule) {
+        const bool had_w = m->w_valid;
         PotrfWork w;
         int64_t p0 = 0;
-        FGP_TRY(prepare_head_work(m, jb, &w, &p0));
+        FGP_TRY(prepare_head_work(m, jb, &w, &p0));  // panel table: the old panels (the last one cut at jb), then the new ones
+        if (had_w && p0 > 0 && Mrows <= m->cap)
+            m->launches += trsm_fwd_t_panels(Arows, m->cap, Mrows, m->L.p, m->cap, m->Wp.p, m->pstart.data(), p0, jb,
+                                             np_new / TILE, m->pbuf[0].p, m->pbuf[1].p, m->ctx(), m->lookahead ? m->st2 : nullptr,
+                                             m->evA, m->evB, m->evC);
+        else
+            m->launches += trsm_fwd_t(Arows, m->cap, Mrows, m->L.p, m->cap, m->inv.p, 0, jb, Arows + jb * TILE * m->cap, m->ctx());
         potrf_lower_head(m->L.p, m->cap, np_new, jb, w, p0, has_eps, eps, m->info_d, m->ctx(), m->lookahead ? &la : nullptr, &cnt);
+        m->w_valid = had_w;
     } else {
+        m->launches += trsm_fwd_t(Arows, m->cap, Mrows, m->L.p, m->cap, m->inv.p, 0, jb, Arows + jb * TILE * m->cap, m->ctx());
         potrf_lower(m->L.p, m->cap, np_new, jb, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->ctx(),
                     m->lookahead ? &la : nullptr, &cnt);
+        m->pstart.clear();
+        m->w_valid = false;
     }
     m->launches += cnt.launches;
     CU(m, cudaMemcpyAsync(m->info_h, m->info_d, sizeof(int), cudaMemcpyDeviceToHost, m->st));
@@ -1050,10 +1068,15 @@ FGP_EXPORT int fgp_shard_plan(int64_t n, int nranks, int rank, int64_t* panel_co
 
 namespace {
 int run_factor_sharded(fgp_model* m, const fgp_kernel_desc* kernel, const KernelTraits& kt, double noise, int has_eps, double eps) {
-    if (!m->head_schedule) return factor_sharded(m, kernel, kt, noise, has_eps, eps);
+    if (!m->head_schedule) {
+        m->pstart.clear();
+        m->w_valid = false;
+        return factor_sharded(m, kernel, kt, noise, has_eps, eps);
+    }
     PotrfWork w;
     int64_t p0 = 0;
     FGP_TRY(prepare_head_work(m, 0, &w, &p0));
+    m->w_valid = false;  // a rank only holds the inverse blocks of the panels it owns
     return factor_sharded_head(m, kernel, kt, noise, has_eps, eps, w);
 }
 

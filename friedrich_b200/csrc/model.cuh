@@ -73,6 +73,7 @@ struct fgp_model {
     int* head_sync = nullptr;              // [head_sync_cap][HEAD_SYNC_INTS]
     int64_t head_sync_cap = 0;
     std::vector<int64_t> pstart;           // first block column of every panel of the current factor (W slot = index)
+    bool w_valid = false;                  // Wp holds the inverse diagonal block of EVERY panel in pstart (single-GPU head fits)
     cudaEvent_t evTop = nullptr, evRest = nullptr, evCopy[2] = {nullptr, nullptr};
     bool head_schedule = true;             // FGP_OPT_HEAD: 0 = the per-block-column schedule of round 1 (A/B runs)
     fgp::DevBuf staging;                   // H2D landing zone (column-major inputs)

@@ -152,8 +152,8 @@ __device__ __noinline__ void head_pivot32(double* T, double* rdiag, int s, int l
         HEAD_MARK(34 + 2 * p);
         // rank-8 update of the columns behind the panel, inside the block: tiles (mi, ni), p < ni <= mi <= 3.  All six lower
         // tiles are computed in one straight-line block (fragments first, then 12 independent DMMAs); tiles of finished
-        // columns (ni <= p) keep their old value.
-        {
+        // columns (ni <= p) keep their old value.  (Nothing is behind the last panel.)
+        if (p < 3) {
             double f[3][2], cv[6][2], acc[6][2];
 #pragma unroll
             for (int m = 0; m < 3; ++m)

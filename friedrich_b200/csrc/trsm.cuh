@@ -111,4 +111,72 @@ inline int64_t trsm_fwd_t_lookahead(double* Xt, int64_t ldx, int64_t M, const do
     return launches;
 }
 
+// The same solve over the PANELS of the head schedule, with the inverse W_p = L11^-1 of every panel's diagonal block
+// (potrf.cuh PotrfWork::W): per panel one out-of-place product  T = Xt[:, panel] W_p^T  (K <= 512, block-triangular W) and
+// one update  Xt[:, later] -= T L[later, panel]^T  (K = panel width): 2 launches per 512 columns instead of 8, all of them at
+// the GEMM kernel's efficient depth.  `tmp0/1` hold M x 512 doubles (ld = M); panel p covers block columns
+// [pstart[p], pstart[p+1]) (pstart[npanels] = i_end).  With a panel stream the NEXT panel's columns are updated first on it and
+// its T product follows at once, while the main stream updates everything behind (one-panel look-ahead as in potrf_lower_head).
+// `upd_end` >= i_end: block columns [i_end, upd_end) are updated like the others but never solved — add_samples: the rows of
+// Xt ARE the new block rows of L, so L[later, panel] for those columns is the panel just solved (copied back before the
+// update reads it) and the new diagonal block receives  -= T T^T  panel by panel, in order (no K = n SYRK at the end).
+// Returns the number of launches; ends joined on st.st.
+inline int64_t trsm_fwd_t_panels(double* Xt, int64_t ldx, int64_t M, const double* L, int64_t ldl, const double* W,
+                                 const int64_t* pstart, int64_t npanels, int64_t i_end, int64_t upd_end, double* tmp0,
+                                 double* tmp1, const LaunchCtx& st, cudaStream_t panel_stream, cudaEvent_t ev_panel,
+                                 cudaEvent_t ev_trail0, cudaEvent_t ev_trail1) {
+    constexpr int64_t WP = 512;
+    int64_t launches = 0;
+    LaunchCtx pc = st;
+    const bool two = panel_stream != nullptr;
+    if (two) pc.st = panel_stream;
+    auto gemm = [&](double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t N, int64_t K,
+                    double alpha, int beta_one, int k_upto, const LaunchCtx& c) {
+        if (N <= 0) return;
+        GemmArgs g{};
+        g.C = C; g.ldc = ldc;
+        g.A = A; g.lda = lda;
+        g.B = B; g.ldb = ldb;
+        g.M = (int)M; g.N = (int)N; g.K = (int)K;
+        g.alpha = alpha; g.beta_one = beta_one; g.lower = 0; g.k_upto_col = k_upto;
+        launches += gemm_nt_launch(g, c) > 0;
+    };
+    auto pend = [&](int64_t p) { return p + 1 < npanels ? pstart[p + 1] : i_end; };
+    if (upd_end < i_end) upd_end = i_end;
+    if (two) {
+        cudaEventRecord(ev_trail0, st.st);  // the panel stream starts after whatever filled Xt on the main stream
+        cudaStreamWaitEvent(panel_stream, ev_trail0, 0);
+    }
+    for (int64_t p = 0; p < npanels; ++p) {
+        const int64_t J = pstart[p], Jend = pend(p), w = (Jend - J) * TILE;
+        double* tmp = (p & 1) ? tmp1 : tmp0;
+        cudaEvent_t ev_trail = (p & 1) ? ev_trail1 : ev_trail0;
+        double* Xp = Xt + J * TILE * ldx;
+        // main-stream update p-2 has read tmp of this parity and brought this panel's columns up to date
+        if (two && p >= 2) cudaStreamWaitEvent(panel_stream, ev_trail, 0);
+        // T = Xt[:, panel] W_p^T ; the solved panel goes back into Xt (a small 2-D copy)
+        gemm(tmp, M, Xp, ldx, W + p * WP * WP, WP, w, w, 1.0, 0, 1, pc);
+        cudaMemcpy2DAsync(Xp, ldx * sizeof(double), tmp, M * sizeof(double), M * sizeof(double), (size_t)w, cudaMemcpyDeviceToDevice,
+                          pc.st);
+        if (Jend >= upd_end) break;
+        // the next panel's columns first (panel stream: its T product follows at once), everything behind them on the main stream
+        const int64_t Jnext = (Jend < i_end) ? pend(p + 1) : Jend;
+        if (two) {
+            cudaEventRecord(ev_panel, panel_stream);
+            gemm(Xt + Jend * TILE * ldx, ldx, tmp, M, L + Jend * TILE + J * TILE * ldl, ldl, (Jnext - Jend) * TILE, w, -1.0, 1, 0, pc);
+            cudaStreamWaitEvent(st.st, ev_panel, 0);
+            gemm(Xt + Jnext * TILE * ldx, ldx, tmp, M, L + Jnext * TILE + J * TILE * ldl, ldl, (upd_end - Jnext) * TILE, w, -1.0, 1, 0,
+                 st);
+            cudaEventRecord(ev_trail, st.st);
+        } else {
+            gemm(Xt + Jend * TILE * ldx, ldx, tmp, M, L + Jend * TILE + J * TILE * ldl, ldl, (upd_end - Jend) * TILE, w, -1.0, 1, 0, st);
+        }
+    }
+    if (two) {
+        cudaEventRecord(ev_panel, panel_stream);
+        cudaStreamWaitEvent(st.st, ev_panel, 0);  // join
+    }
+    return launches;
+}
+
 }  // namespace fgp
