@@ -94,6 +94,7 @@ SIGNATURES = {
     "fgp_comm_destroy": (C.c_int, [_h]),
     "fgp_fit_sharded": (C.c_int, [_h, _dp, _i64, _i64, _i64, _dp, _kd, C.c_double, C.c_int, C.c_double]),
     "fgp_refit_sharded": (C.c_int, [_h, _kd, C.c_double, C.c_int, C.c_double]),
+    "fgp_lml_gradient_sharded": (C.c_int, [_h, _kd, C.c_double, C.c_int, _dp, _dp]),
     "fgp_shard_plan": (C.c_int, [_i64, C.c_int, C.c_int, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), _dp]),
     "fgp_comm_last_bytes": (C.c_double, [_h]),
     "fgp_alloc_pinned": (C.c_void_p, [C.c_size_t]),

@@ -32,6 +32,8 @@ using namespace fgp;
 
 namespace {
 
+int comm_agree(fgp_model* m, int local_rc);  // cross-rank status exchange before a collective part (defined with the sharded entry points)
+
 // upload a column-major host matrix (rows x cols, ld) compactly into m->staging (ld = rows)
 int upload_colmajor(fgp_model* m, const double* src, int64_t ld, int64_t rows, int64_t cols) {
     CU(m, m->staging.reserve((size_t)rows * cols));
@@ -403,7 +405,7 @@ FGP_EXPORT int fgp_destroy(fgp_model* m) {
         comm_release(m);
         for (DevBuf* b : {&m->xr, &m->xc, &m->nc, &m->nr, &m->cmean, &m->y, &m->z, &m->alpha, &m->work, &m->L, &m->inv,
                           &m->invT, &m->staging, &m->qr, &m->qc, &m->qnc, &m->qnr, &m->bt, &m->partial, &m->mean_d,
-                          &m->var_d, &m->scalars, &m->kqq, &m->U, &m->Kinv, &m->lml_partial, &m->Wp, &m->Pscr, &m->pbuf[0],
+                          &m->var_d, &m->scalars, &m->kqq, &m->U, &m->Kinv, &m->lml_partial, &m->lml_rows, &m->Wp, &m->Pscr, &m->pbuf[0],
                           &m->pbuf[1]})
             b->release();
         if (m->head_sync) cudaFree(m->head_sync);
@@ -685,6 +687,27 @@ FGP_EXPORT int fgp_lml_gradient(fgp_model* m, const fgp_kernel_desc* kernel, dou
     FGP_TRY(check_kernel(m, kernel, &kt));
     begin_timed(m);
     int rc = lml_gradient_device(m, kernel, kt, noise, scaled, scale_out, grads);
+    int rc2 = end_timed(m);
+    return rc != FGP_OK ? rc : rc2;
+}
+
+// The same gradient, collectively: every rank of the communicator calls it after fgp_fit_sharded / fgp_refit_sharded (all
+// hold the full factor); the O(n^3) inverse is split over the ranks (csrc/lml.cu) and every rank returns the same values.
+FGP_EXPORT int fgp_lml_gradient_sharded(fgp_model* m, const fgp_kernel_desc* kernel, double noise, int scaled, double* scale_out,
+                                        double* grads) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (!m->comm) return fail(m, FGP_ERR_COMM, "fgp_comm_init_rank has not been called");
+    KernelTraits kt;
+    begin_timed(m);
+    const auto local = [&]() -> int {
+        if (!m->fitted) return fail(m, FGP_ERR_NOT_FITTED, "model is not fitted");
+        if (!grads) return fail(m, FGP_ERR_BAD_ARG, "null output");
+        return check_kernel(m, kernel, &kt);
+    };
+    FGP_TRY(comm_agree(m, local()));
+    int rc = lml_gradient_sharded_device(m, kernel, kt, noise, scaled, scale_out, grads);
     int rc2 = end_timed(m);
     return rc != FGP_OK ? rc : rc2;
 }
@@ -1046,7 +1069,8 @@ FGP_EXPORT double fgp_comm_last_bytes(const fgp_model* m) { return (m && m->comm
 FGP_EXPORT int fgp_shard_plan(int64_t n, int nranks, int rank, int64_t* panel_cols, int64_t* n_panels, int64_t* n_owned,
                               double* flop_share) {
     if (n <= 0 || nranks < 1 || rank < 0 || rank >= nranks) return FGP_ERR_BAD_ARG;
-    const int64_t np = round_up(n, TILE), nb = np / TILE, PANEL_TILES = panel_tiles(np, nranks), NP = (nb + PANEL_TILES - 1) / PANEL_TILES;
+    // the head schedule (default) uses 512-column panels whatever the size and the number of ranks
+    const int64_t np = round_up(n, TILE), nb = np / TILE, PANEL_TILES = HEAD_PANEL / TILE, NP = (nb + PANEL_TILES - 1) / PANEL_TILES;
     int64_t owned = 0;
     double mine = 0.0, total = 0.0;
     for (int64_t p = 0; p < NP; ++p) {

@@ -51,7 +51,7 @@ gemm_nt_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ CUten
     gemm_tile_decode(g, blockIdx.x / S::SUBS, ti, tj);
     const int sub = blockIdx.x % S::SUBS;
     const int m0 = ti * GEMM_BM + sub * CM, n0 = tj * GEMM_BN;
-    const int kbeg = g.k_from_tile ? GEMM_BM * max(ti, tj) : 0;
+    const int kbeg = g.k_from_tile ? GEMM_BM * (g.k_tile0 + max(ti, tj)) : 0;
     const int kend = g.k_upto_col ? min(g.K, GEMM_BN * (tj + 1)) : g.K;
     const int nk = (kend - kbeg) / GEMM_KC;
     const bool diag_tile = g.lower && (ti == tj);
@@ -298,10 +298,16 @@ int64_t gemm_nt_tiles(const GemmArgs& g) {
 }
 
 double gemm_nt_flops(const GemmArgs& g) {
-    if (g.k_from_tile) {  // U U^T on upper-triangular operands: tile (i, j<=i) contracts over K - 128 i
-        const int tm = g.M / GEMM_BM;
+    if (g.k_from_tile) {  // U U^T on upper-triangular operands: tile (i, j<=i) contracts over K - 128 (k_tile0 + i)
+        GemmArgs p = g;
+        gemm_nt_plan(p);
+        const int64_t tiles = gemm_nt_tiles(g);
         double f = 0.0;
-        for (int i = 0; i < tm; ++i) f += (double)(i + 1) * (g.K - GEMM_BM * i);
+        for (int64_t b = 0; b < tiles; ++b) {
+            int ti, tj;
+            gemm_tile_decode(p, (int)b, ti, tj);
+            f += (double)(g.K - GEMM_BM * (g.k_tile0 + std::max(ti, tj)));
+        }
         return 2.0 * GEMM_BM * GEMM_BN * f;
     }
     if (g.k_upto_col && !g.lower) {  // A W^T with W lower block-triangular: tile column j contracts over min(K, 128 (j + 1))

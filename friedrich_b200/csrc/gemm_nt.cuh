@@ -72,6 +72,8 @@ struct GemmArgs {
                      //    are `stride` tile columns apart (0,0 = contiguous); rows/columns are relative to C, whose origin
                      //    is on the diagonal
     int k_from_tile; // 1: contraction starts at k = 128*max(tile_row, tile_col) (operands upper-triangular: U U^T)
+    int k_tile0;     // k_from_tile: tile index of C's origin on the diagonal of the full matrix (the contraction of tile (ti, tj)
+                     //    starts at k = 128*(k_tile0 + max(ti, tj)): a rank's share of K^-1 = U U^T starts at its first owned panel)
     int k_upto_col;  // 1: contraction ends at k = 128*(tile_col + 1) (B lower block-triangular: the panel solve A W^T, W = L11^-1)
     int row_skip;    // lower mode: the first row_skip tile rows are not computed (the diagonal block of the next panel is
                      //    updated by a separate, earlier launch on the panel stream)

@@ -1,6 +1,9 @@
 // lml.cu — LML-gradient reductions and the bandwidth heuristic on the pair-tile engine (contract in lml.cuh).
 #include "lml.cuh"
 
+#include "potrf.cuh"
+#include "sharded.cuh"
+
 namespace fgp {
 
 template <int KIND, int PMAX>
@@ -159,6 +162,133 @@ int lml_gradient_device(fgp_model* m, const fgp_kernel_desc* kd, const KernelTra
     if (!scaled) grads[P] = noise * (h[50] - h[2 * pmax]);      // optimizer.rs:54-57
     if (scale_out) *scale_out = scale;
     m->kinv_valid = true;
+    return FGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same gradient with the O(n^3) work spread over the ranks of the communicator (every rank holds the full factor after
+// fgp_fit_sharded):
+//   1. U = L^-T by ROWS: the rows of the forward solve on the identity are independent, rank r takes the block rows
+//      r, r+P, ... (cyclic: equal shares of the triangle), n^3 / (3 P) flops and no communication;
+//   2. ncclAllGather of the row shares (8 n^2 / 2 bytes in total) + a local un-permutation into the natural layout;
+//   3. K^-1 = U U^T on the tile columns of the 512-column panels the rank owns in the fit's distribution (one lower-mode
+//      launch, k_from_tile), n^3 / (3 P) flops;
+//   4. the pair-tile reductions over the owned columns, then ONE ncclAllReduce of the 2 P + 1 partial sums.
+__global__ void set_cyclic_identity_kernel(double* Xt, int64_t ld, int64_t nblocks, int64_t first, int64_t stride) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // local row
+    if (i >= nblocks * TILE) return;
+    const int64_t t = i / TILE, b = first + t * stride;
+    Xt[i + (b * TILE + i % TILE) * ld] = 1.0;
+}
+// U[(b*128 + i), c] = Ug[rank b % P][(b / P)*128 + i, c]  (chunk leading dimension mmax)
+__global__ void unpermute_rows_kernel(const double* __restrict__ Ug, int64_t mmax, int64_t np, int P, double* __restrict__ U) {
+    const int64_t c = blockIdx.y;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < np; row += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = row / TILE, i = row % TILE;
+        U[row + c * np] = Ug[(size_t)(b % P) * mmax * np + (b / P) * TILE + i + c * mmax];
+    }
+}
+
+int lml_gradient_sharded_device(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& kt, double noise, int scaled,
+                                double* scale_out, double* grads) {
+    fgp_comm* cm = m->comm;
+    const int P = cm->nranks, r = cm->rank;
+    // (a communicator of ONE rank runs the very same steps with the two collectives replaced by a copy / nothing, so that the
+    // schedule is testable on a single GPU)
+    const NcclApi* nccl = (P > 1) ? nccl_api() : nullptr;
+    if (P > 1 && !nccl) return fail(m, FGP_ERR_COMM, "libnccl.so.2 could not be loaded");
+    const int64_t np = m->np, nb = np / TILE;
+    const int np_params = kt.nparams;
+    const int64_t tmax = (nb + P - 1) / P, mmax = tmax * TILE;            // block rows per rank (padded to the largest share)
+    const int64_t mine = (nb > r) ? (nb - r + P - 1) / P : 0;              // block rows r, r+P, ... < nb
+    // 1. my rows of U (mmax x np, ld mmax); rows beyond my share stay zero
+    CU(m, m->lml_rows.reserve((size_t)mmax * np));
+    CU(m, m->U.reserve((size_t)np * np));
+    CU(m, m->Kinv.reserve((size_t)np * np + (size_t)P * mmax * np));      // K^-1, then the gather buffer
+    double* Ug = m->Kinv.p + (size_t)np * np;
+    CU(m, cudaMemsetAsync(m->lml_rows.p, 0, (size_t)mmax * np * sizeof(double), m->st));
+    if (mine > 0)
+        set_cyclic_identity_kernel<<<(unsigned)((mine * TILE + 255) / 256), 256, 0, m->st>>>(m->lml_rows.p, mmax, mine, r, P);
+    m->launches += 1;
+    m->launches += trsm_fwd_t(m->lml_rows.p, mmax, mine * TILE, m->L.p, m->cap, m->inv.p, 0, nb, nullptr, m->ctx(), true, r, P);
+    // 2. all ranks' rows, then the natural layout
+    if (P > 1) {
+        if (nccl->AllGather(m->lml_rows.p, Ug, (size_t)mmax * np, ncclDouble, cm->comm, m->st) != ncclSuccess)
+            return fail(m, FGP_ERR_COMM, "ncclAllGather of the rows of L^-T failed");
+    } else {
+        CU(m, cudaMemcpyAsync(Ug, m->lml_rows.p, (size_t)mmax * np * sizeof(double), cudaMemcpyDeviceToDevice, m->st));
+    }
+    unpermute_rows_kernel<<<dim3(8, (unsigned)np), 256, 0, m->st>>>(Ug, mmax, np, P, m->U.p);
+    m->launches += 1;
+    // 3. K^-1 on the owned panels: tile columns [4 p, 4 p + 4) for p = r, r+P, ...
+    const int64_t PT = HEAD_PANEL / TILE, NPn = (nb + PT - 1) / PT;
+    int64_t ncols = 0;
+    for (int64_t p = r; p < NPn; p += P) ncols += std::min<int64_t>(PT, nb - p * PT);
+    if (ncols > 0) {
+        const int64_t c0 = (int64_t)r * PT;
+        GemmArgs g{};
+        g.C = m->Kinv.p + c0 * TILE * (np + 1); g.ldc = np;
+        g.A = m->U.p + c0 * TILE; g.lda = np;
+        g.B = g.A; g.ldb = np;
+        g.M = (int)(np - c0 * TILE); g.N = (int)(ncols * TILE); g.K = (int)np;
+        g.alpha = 1.0; g.beta_one = 0; g.lower = 1; g.k_from_tile = 1; g.k_tile0 = (int)c0;
+        g.grp = (int)PT; g.stride = (int)(P * PT);
+        m->launches += gemm_nt_launch(g, m->ctx()) > 0;
+    }
+    // 4. reductions over the owned columns: one pair-tile launch per owned panel, partials laid out one after the other
+    const DevKernel dk = to_dev(kd);
+    const int mode = (kt.need_d2 ? PAIR_D2 : 0) | (kt.need_dot ? PAIR_DOT : 0);
+    const bool fast = (kt.kind == KIND_SQEXP || kt.kind == KIND_MATERN2);
+    const int pmax = fast ? 2 : FGP_MAX_PARAMS, nv = 2 * pmax + 1;
+    int64_t blocks = 0;
+    for (int64_t p = r; p < NPn; p += P) {
+        const int64_t w = std::min<int64_t>(PT, nb - p * PT);
+        blocks += (nb - p * PT) * (w * TILE / PAIR_TN);
+    }
+    CU(m, m->lml_partial.reserve((size_t)std::max<int64_t>(blocks, 1) * nv));
+    int64_t off = 0;
+    for (int64_t p = r; p < NPn; p += P) {
+        const int64_t w = std::min<int64_t>(PT, nb - p * PT);
+        PairArgs pa{};
+        pa.xa_c = pa.xb_c = m->xc.p;
+        pa.xa_r = pa.xb_r = m->xr.p;
+        pa.na = pa.nb = m->nc.p;
+        pa.dp = (int)m->dp;
+        pa.rows = pa.cols = np;
+        pa.row_tile0 = (int)(p * PT);
+        pa.col_tile0 = (int)(p * PT * TILE / PAIR_TN);
+        pa.col_tiles = (int)(w * TILE / PAIR_TN);
+        pa.symmetric = 1;
+        double* part = m->lml_partial.p + off * nv;
+        if (kt.kind == KIND_SQEXP) launch_lml<KIND_SQEXP, 2, PAIR_D2>(m, pa, dk, m->Kinv.p, np, part);
+        else if (kt.kind == KIND_MATERN2) launch_lml<KIND_MATERN2, 2, PAIR_D2>(m, pa, dk, m->Kinv.p, np, part);
+        else if (mode == PAIR_D2) launch_lml<KIND_GENERIC, FGP_MAX_PARAMS, PAIR_D2>(m, pa, dk, m->Kinv.p, np, part);
+        else if (mode == PAIR_DOT) launch_lml<KIND_GENERIC, FGP_MAX_PARAMS, PAIR_DOT>(m, pa, dk, m->Kinv.p, np, part);
+        else launch_lml<KIND_GENERIC, FGP_MAX_PARAMS, PAIR_BOTH>(m, pa, dk, m->Kinv.p, np, part);
+        const dim3 grid = pair_grid(pa);
+        off += (int64_t)grid.x * grid.y;
+    }
+    CU(m, m->scalars.reserve(64));
+    CU(m, cudaMemsetAsync(m->scalars.p, 0, 64 * sizeof(double), m->st));
+    if (off > 0) partials_final_kernel<<<1, 64, 0, m->st>>>(m->lml_partial.p, off, nv, m->scalars.p);
+    if (P > 1 && nccl->AllReduce(m->scalars.p, m->scalars.p, (size_t)nv, ncclDouble, ncclSum, cm->comm, m->st) != ncclSuccess)
+        return fail(m, FGP_ERR_COMM, "ncclAllReduce of the gradient sums failed");
+    reduce_kernel<2><<<1, 256, 0, m->st>>>(m->alpha.p, m->alpha.p, m->n, dk, 0.0, m->scalars.p + 50);  // alpha.alpha
+    reduce_kernel<2><<<1, 256, 0, m->st>>>(m->y.p, m->alpha.p, m->n, dk, 0.0, m->scalars.p + 51);      // y.alpha
+    m->launches += 3;
+    FGP_TRY(ensure_pinned(m, 64));
+    CU(m, cudaMemcpyAsync(m->pinned, m->scalars.p, 52 * sizeof(double), cudaMemcpyDeviceToHost, m->st));
+    CU(m, cudaStreamSynchronize(m->st));
+    const double* h = m->pinned;
+    const double scale = scaled ? h[51] / (double)m->n : 1.0;  // optimizer.rs:174
+    for (int p = 0; p < np_params; ++p) {
+        double data_fit = h[pmax + p];
+        if (scaled) data_fit /= scale;                          // optimizer.rs:186
+        grads[p] = (data_fit - h[p]) / 2.0;                     // optimizer.rs:192 / :49
+    }
+    if (!scaled) grads[np_params] = noise * (h[50] - h[2 * pmax]);  // optimizer.rs:54-57
+    if (scale_out) *scale_out = scale;
+    m->kinv_valid = false;  // only this rank's panels of K^-1 are on the device
     return FGP_OK;
 }
 

@@ -26,6 +26,9 @@ namespace fgp {
 // defined in lml.cu
 int lml_gradient_device(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& kt, double noise, int scaled,
                         double* scale_out, double* grads);
+// collective: every rank of the model's communicator (all hold the full factor); same result on every rank
+int lml_gradient_sharded_device(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& kt, double noise, int scaled,
+                                double* scale_out, double* grads);
 int mean_pair_distance_device(fgp_model* m, double* out);
 // A[i + i*ld] = 1 for i < n
 void launch_set_identity(double* A, int64_t ld, int64_t n, cudaStream_t st);

@@ -92,7 +92,7 @@ struct fgp_model {
     bool force_batched_predict = false;    // fgp_predict_cov needs the transposed solve buffer whatever q is
 
     // LML workspace -------------------------------------------------------------------------------------------
-    fgp::DevBuf U, Kinv, lml_partial;
+    fgp::DevBuf U, Kinv, lml_partial, lml_rows;
     bool kinv_valid = false;               // Kinv holds K^-1 of the CURRENT factor (set by fgp_lml_gradient, cleared by every refit)
 
     // multi-GPU -----------------------------------------------------------------------------------------------

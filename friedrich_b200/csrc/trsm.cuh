@@ -19,11 +19,16 @@
 namespace fgp {
 
 // returns the number of kernel launches
+// `tri_first` / `tri_stride` (with tri_rows): the rows of Xt are the identity rows of the block rows tri_first, tri_first +
+// tri_stride, ... only (a rank's share of U = L^-T in the sharded LML gradient): block column i is then non-zero in the first
+// 128 * #{owned block rows <= i} rows.
 inline int64_t trsm_fwd_t(double* Xt, int64_t ldx, int64_t M, const double* L, int64_t ldl, const double* inv,
-                          int64_t i_begin, int64_t i_end, double* trailing, const LaunchCtx& st, bool tri_rows = false) {
+                          int64_t i_begin, int64_t i_end, double* trailing, const LaunchCtx& st, bool tri_rows = false,
+                          int64_t tri_first = 0, int64_t tri_stride = 1) {
     int64_t launches = 0;
     for (int64_t i = i_begin; i < i_end; ++i) {
-        const int64_t Mi = tri_rows ? std::min<int64_t>(M, (i + 1) * TILE) : M;
+        const int64_t Mi = tri_rows ? std::min<int64_t>(M, (i >= tri_first ? (i - tri_first) / tri_stride + 1 : 0) * TILE) : M;
+        if (Mi <= 0) continue;
         {
             GemmArgs g{};
             g.C = Xt + i * TILE * ldx; g.ldc = ldx;

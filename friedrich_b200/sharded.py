@@ -69,3 +69,13 @@ def fit_sharded(handle, X, y_resid, kernel_desc, noise, cholesky_epsilon=None):
 def refit_sharded(handle, kernel_desc, noise, cholesky_epsilon=None):
     has_eps, eps = (0, 0.0) if cholesky_epsilon is None else (1, float(cholesky_epsilon))
     handle.check(N.lib().fgp_refit_sharded(handle.ptr, C.byref(kernel_desc), float(noise), has_eps, eps))
+
+
+def lml_gradient_sharded(handle, kernel_desc, noise, nparams, scaled=True):
+    """Collective `fgp_lml_gradient_sharded` (every rank calls it after the sharded fit): (scale, grads) as the reference's
+    scaled_gradient_marginal_likelihood (optimizer.rs:159-203), or (1.0, grads + [noise gradient]) for scaled=False."""
+    grads = np.zeros(nparams + 1)
+    scale = C.c_double(1.0)
+    handle.check(N.lib().fgp_lml_gradient_sharded(handle.ptr, C.byref(kernel_desc), float(noise), 1 if scaled else 0,
+                                                  C.cast(C.byref(scale), N._dp), N.dptr(grads)))
+    return scale.value, (list(grads[:nparams]) if scaled else list(grads))

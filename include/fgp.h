@@ -132,14 +132,19 @@ int fgp_cholesky_lower(int device, double* A, int64_t lda, int64_t n, int64_t* f
 /* multi-GPU fit (no reference counterpart: the crate is single-threaded) ---------------------------
  * One process per GPU.  The 512-column panels of the covariance matrix are owned block-cyclically; each rank assembles
  * only its own panels (algebra/mod.rs:70-79 restricted to them), the owner of a panel factors it and ncclBroadcast()s it
- * over NVLink 128 columns at a time while it factors on, every rank applies it to the panels it owns (one-panel
- * look-ahead).  With one rank the panels are 1024 columns wide from n = 24576 on.  When the call returns EVERY rank
- * holds the complete factor and alpha, so predict / likelihood / lml_gradient run locally (queries shard trivially).
+ * over NVLink, every rank applies it to the panels it owns (one-panel look-ahead; csrc/sharded.cu).  The arithmetic per tile
+ * is that of the single-GPU fit (same 512-column panels, same head kernel), so the factors agree bit for bit at any size.
+ * When the call returns EVERY rank holds the complete factor and alpha, so predict / likelihood run locally (queries shard
+ * trivially) and fgp_lml_gradient_sharded splits the O(n^3) inverse over the ranks.
  * fgp_comm_unique_id   rank 0: ncclGetUniqueId into a caller buffer of FGP_COMM_ID_BYTES bytes; the caller ships it to
  *                      the other processes (bench.py: torch.distributed broadcast — plumbing only).
  * fgp_comm_init_rank   every rank: ncclCommInitRank on the handle's GPU.  nranks == 1 needs no id exchange.
  * fgp_fit_sharded      fgp_fit, collectively. X / y_resid are read on rank 0 (others may pass NULL) and broadcast.
  * fgp_refit_sharded    fgp_refit, collectively (inputs already resident on every rank).
+ * fgp_lml_gradient_sharded  fgp_lml_gradient, collectively (optimizer.rs:24-60, :159-203 on a sharded model): U = L^-T by
+ *                      block rows r, r+P, .. (no communication), ncclAllGather of the rows, K^-1 = U U^T on the owned panels,
+ *                      pair-tile reductions on the owned columns, one ncclAllReduce of the partial sums.  Same values on
+ *                      every rank.
  * fgp_shard_plan       host-only: panel width, panel count, panels owned by `rank`, its share of the update flops.
  * fgp_comm_last_bytes  bytes this rank sent or received in panel broadcasts during the last sharded factorisation. */
 #define FGP_COMM_ID_BYTES 128
@@ -149,6 +154,8 @@ int fgp_comm_destroy(fgp_model* m);
 int fgp_fit_sharded(fgp_model* m, const double* X, int64_t ldx, int64_t n, int64_t d, const double* y_resid,
                     const fgp_kernel_desc* kernel, double noise, int has_eps, double eps);
 int fgp_refit_sharded(fgp_model* m, const fgp_kernel_desc* kernel, double noise, int has_eps, double eps);
+int fgp_lml_gradient_sharded(fgp_model* m, const fgp_kernel_desc* kernel, double noise, int scaled, double* scale_out,
+                             double* grads);
 int fgp_shard_plan(int64_t n, int nranks, int rank, int64_t* panel_cols, int64_t* n_panels, int64_t* n_owned,
                    double* flop_share);
 double fgp_comm_last_bytes(const fgp_model* m);

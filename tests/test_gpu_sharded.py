@@ -72,3 +72,32 @@ def test_sharded_fit_without_communicator_is_an_error():
     with pytest.raises(N.FgpError) as e:
         sharded.fit_sharded(h, X, y, SquaredExp(1.0, 1.0).device_desc(), 0.1)
     assert e.value.code == N.FGP_ERR_COMM
+
+
+@pytest.mark.parametrize("n,d,kname", [(300, 3, "sqexp"), (1100, 4, "matern2"), (2049, 5, "sqexp")])
+def test_single_rank_sharded_lml_gradient_matches_plain_and_oracle(n, d, kname):
+    """fgp_lml_gradient_sharded on a communicator of one rank runs the sharded schedule itself (cyclic rows of L^-T, gather
+    layout, K^-1 on owned panels with k_tile0, per-panel reductions) — against the single-GPU entry point and the oracle."""
+    N, sharded, SquaredExp, Matern2, make_dataset, O = _mods()
+    X, y = make_dataset(6000 + n, n, d)
+    ls = math.sqrt(d / 6.0)
+    kern = SquaredExp(ls, 1.0) if kname == "sqexp" else Matern2(ls, 1.0)
+    okd = O.KernelDesc.make([O.K_SQUARED_EXP if kname == "sqexp" else O.K_MATERN2], [ls, 1.0])
+    kd = kern.device_desc()
+    hs, hp = N.Handle(0), N.Handle(0)
+    sharded.comm_init(hs, 0, 1)
+    sharded.fit_sharded(hs, X, y, kd, 0.1)
+    hp.check(N.lib().fgp_fit(hp.ptr, N.dptr(N.fcol(X)), n, n, d, N.dptr(y), C.byref(kd), 0.1, 0, 0.0))
+    scale_s, g_s = sharded.lml_gradient_sharded(hs, kd, 0.1, 2, scaled=True)
+    g_p, scale_p = np.zeros(3), C.c_double(1.0)
+    hp.check(N.lib().fgp_lml_gradient(hp.ptr, C.byref(kd), 0.1, 1, C.cast(C.byref(scale_p), N._dp), N.dptr(g_p)))
+    assert abs(scale_s - scale_p.value) <= 1e-12 * abs(scale_p.value)
+    assert np.allclose(g_s, g_p[:2], rtol=1e-10, atol=1e-12)
+    _, gu_s = sharded.lml_gradient_sharded(hs, kd, 0.1, 2, scaled=False)
+    gu_p = np.zeros(3)
+    hp.check(N.lib().fgp_lml_gradient(hp.ptr, C.byref(kd), 0.1, 0, None, N.dptr(gu_p)))
+    assert np.allclose(gu_s, gu_p, rtol=1e-10, atol=1e-12)
+    if n <= 1200:
+        ref = O.OracleGaussianProcess(O.ZeroPrior(), okd, 0.1, None, X, y)
+        sr, gr = ref.gradient_marginal_likelihood(scaled=True)
+        assert abs(scale_s - sr) < 1e-9 * abs(sr) and np.allclose(g_s, gr, rtol=1e-8, atol=1e-9)

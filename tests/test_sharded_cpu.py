@@ -16,7 +16,7 @@ def test_plan_partitions_every_panel_exactly_once(n, world):
     plans = [sharded.shard_plan(n, world, r) for r in range(world)]
     n_panels = plans[0]["n_panels"]
     tiles = -(-n // 128)
-    pt = 8 if (world == 1 and tiles * 128 >= 24576) else 4  # csrc/potrf.cuh panel_tiles(): 1024 columns only on one GPU
+    pt = 4  # csrc/potrf.cuh HEAD_PANEL: 512-column panels on any number of GPUs (so sharded and single-GPU factors agree bit for bit)
     assert plans[0]["panel_cols"] == 128 * pt
     assert n_panels == -(-tiles // pt)
     owned = sorted(p for pl in plans for p in pl["owned"])

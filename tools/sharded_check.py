@@ -40,7 +40,12 @@ h.check(N.lib().fgp_download_factor(h.ptr, N.dptr(L), n))
 mean, var = np.zeros(256), np.zeros(256)
 h.check(N.lib().fgp_predict_mean_var(h.ptr, C.byref(kd), N.dptr(N.fcol(Xq)), 256, 256, N.dptr(mean), N.dptr(var)))
 digest = float(np.sum(np.tril(L) * np.linspace(1.0, 2.0, n)[:, None]))
-out = {"rank": rank, "world": world, "n": n, "d": d, "fit_device_ms": ms, "bcast_mb": N.lib().fgp_comm_last_bytes(h.ptr) / 1e6,
+# the LML gradient, collectively (scaled and unscaled), timed on the second call
+for _ in range(2):
+    gscale, ggrads = sharded.lml_gradient_sharded(h, kd, 0.1, 2, scaled=True)
+grad_ms = h.last_device_ms()
+_, ggrads_u = sharded.lml_gradient_sharded(h, kd, 0.1, 2, scaled=False)
+out = {"rank": rank, "world": world, "n": n, "d": d, "fit_device_ms": ms, "lml_scale": gscale, "lml_grads": ggrads, "bcast_mb": N.lib().fgp_comm_last_bytes(h.ptr) / 1e6,
        "digest": digest}
 if rank == 0:
     hp = N.Handle(local)
@@ -49,6 +54,17 @@ if rank == 0:
     hp.check(N.lib().fgp_download_factor(hp.ptr, N.dptr(Lp), n))
     out["bitwise_equal_single_gpu"] = bool(np.array_equal(np.tril(L), np.tril(Lp)))
     out["single_gpu_ms"] = hp.last_device_ms()
+    g1 = np.zeros(3)
+    s1 = C.c_double(1.0)
+    for _ in range(2):
+        hp.check(N.lib().fgp_lml_gradient(hp.ptr, C.byref(kd), 0.1, 1, C.cast(C.byref(s1), N._dp), N.dptr(g1)))
+    out["lml_gradient_single_gpu_ms"] = hp.last_device_ms()
+    out["lml_gradient_sharded_ms"] = grad_ms
+    out["lml_scale_rel_diff"] = abs(gscale - s1.value) / abs(s1.value)
+    out["lml_grads_max_rel_diff"] = float(np.max(np.abs(np.array(ggrads) - g1[:2]) / np.maximum(np.abs(g1[:2]), 1e-300)))
+    gu = np.zeros(3)
+    hp.check(N.lib().fgp_lml_gradient(hp.ptr, C.byref(kd), 0.1, 0, None, N.dptr(gu)))
+    out["lml_unscaled_grads_max_rel_diff"] = float(np.max(np.abs(np.array(ggrads_u) - gu) / np.maximum(np.abs(gu), 1e-300)))
     if n <= 4096:
         from oracle import oracle as O
         ref = O.OracleGaussianProcess(O.ZeroPrior(), O.KernelDesc.make([O.K_SQUARED_EXP], [ls, 1.0]), 0.1, None, X, y)
