@@ -234,7 +234,8 @@ PairArgs query_pair_args(const fgp_model* m) {
 // the multi-RHS solve costs ~10 ms however few right-hand sides there are, a wavefront forward substitution per query 0.4 ms.
 //   Kc (np x q, one query per COLUMN) = k(train, query);  mean_i = Kc[:, i] . alpha;  z_i = L^-1 Kc[:, i] in place;
 //   var_i = k(q_i, q_i) - ||z_i||^2                                                            (mod.rs:235-241, :260-270)
-constexpr int64_t PREDICT_SMALL_Q = 16;
+constexpr int64_t PREDICT_SMALL_Q = 12;  // measured at n = 16384: 0.45 ms (q = 1) .. 2.3 ms (q = 12); the tensor-pipe path: 2.5 ms
+static_assert(PREDICT_SMALL_Q <= TRSV_MULTI_QMAX, "latency path of predict: right-hand sides per wavefront launch");
 int predict_small(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& kt, int want_mean, int want_var) {
     const int64_t qp = m->qp, np = m->np, q = m->q;
     const int nb = (int)(np / TILE);
@@ -255,14 +256,23 @@ int predict_small(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& k
         m->have_mean = true;
     }
     if (want_var) {
-        int* flags = reinterpret_cast<int*>(m->work.p);  // np doubles of scratch >= q * (nb flags + 1 ticket) for q <= 16
-        CU(m, cudaMemsetAsync(flags, 0, (size_t)q * (nb + 1) * sizeof(int), m->st));
-        for (int64_t i = 0; i < q; ++i)
-            trsv_fwd_wave_kernel<<<nb, TRSV_THREADS, TRSV_WAVE_SMEM, m->st>>>(m->L.p, m->cap, m->inv.p, Kc + i * np, Kc + i * np,
-                                                                            flags + i * (nb + 1), flags + i * (nb + 1) + nb);
+        int* flags = reinterpret_cast<int*>(m->work.p);  // np doubles of scratch >= nb flags + 1 ticket
+        CU(m, cudaMemsetAsync(flags, 0, (size_t)(nb + 1) * sizeof(int), m->st));
+        static bool attr_done_dev[64] = {};
+        bool& attr_done = *per_device_flag(attr_done_dev);
+        if (!attr_done) {
+            cudaFuncSetAttribute(trsv_fwd_wave_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_MULTI_SMEM);
+            attr_done = true;
+        }
+        // ONE wavefront launch for all the right-hand sides (a launch per query costs q x 0.45 ms at n = 16384)
+        if (q == 1)
+            trsv_fwd_wave_kernel<<<nb, TRSV_THREADS, TRSV_WAVE_SMEM, m->st>>>(m->L.p, m->cap, m->inv.p, Kc, Kc, flags, flags + nb);
+        else
+            trsv_fwd_wave_multi_kernel<<<nb, TRSV_THREADS, TRSV_MULTI_SMEM, m->st>>>(m->L.p, m->cap, m->inv.p, Kc, np, (int)q,
+                                                                                   flags, flags + nb);
         col_reduce_kernel<1><<<(unsigned)q, 256, 0, m->st>>>(Kc, np, nullptr, np, m->partial.p + qp);
         rowreduce_final_kernel<<<(unsigned)(qp / 128), 128, 0, m->st>>>(m->partial.p + qp, 1, qp, q, 1, dk, m->qnr.p, m->var_d.p);
-        m->launches += q + 2;
+        m->launches += 3;
         m->have_var = true;
     }
     return FGP_OK;

@@ -172,6 +172,78 @@ trsv_fwd_wave_kernel(const double* __restrict__ L, int64_t ld, const double* __r
     wave_publish(flags + i);
 }
 
+// Forward solve for up to 16 right-hand sides AT ONCE (the latency path of predict for a handful of queries: one launch
+// and one walk over L instead of one per query).  X is np x q (one right-hand side per column, ld = ldx), solved in place.
+// Same ticket / flag protocol as above; a block publishes after all its q segments are written.  Thread (r, h) = (tid & 127,
+// tid >> 7) holds row r, columns 32 h .. 32 h + 31 of the current L tile in registers (loaded once per step, before the
+// wait) and applies it to every right-hand side; the x values are warp-uniform shared-memory broadcasts, the four column
+// quarters meet in shared memory.  (Per step and right-hand side the SM has 128 x 128 FMAs to do: 256 cycles at its fp64 rate.)
+constexpr int TRSV_MULTI_QMAX = 16;
+constexpr int TRSV_MULTI_SMEM = TRSV_WAVE_SMEM + (TRSV_MULTI_QMAX * 128 + TRSV_MULTI_QMAX * 512) * 8;
+static __global__ void __launch_bounds__(TRSV_THREADS)
+trsv_fwd_wave_multi_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ inv, double* X, int64_t ldx, int q,
+                           int* flags, int* ticket) {
+    extern __shared__ __align__(128) unsigned char wave_smem[];
+    double* inv_s = reinterpret_cast<double*>(wave_smem);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(wave_smem + 128 * 128 * 8);
+    double* xs = reinterpret_cast<double*>(wave_smem + TRSV_WAVE_SMEM);  // [QMAX][128]
+    double* red = xs + TRSV_MULTI_QMAX * 128;                            // [QMAX][4][128]
+    __shared__ int s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int tid = threadIdx.x, r = tid & 127, h = tid >> 7;
+    const int i = s_ticket;
+    const int64_t row0 = (int64_t)i * 128;
+    wave_fetch_tile(inv_s, inv + (int64_t)i * 128 * 128, bar);
+    double acc[TRSV_MULTI_QMAX];  // threads 0..127: the running right-hand sides of row r
+#pragma unroll
+    for (int j = 0; j < TRSV_MULTI_QMAX; ++j) acc[j] = (j < q && h == 0) ? X[row0 + r + (int64_t)j * ldx] : 0.0;
+    for (int jb = 0; jb < i; ++jb) {
+        double v[32];  // independent of x_jb: in flight while we wait for it
+        tile_load_512(L + row0 + (int64_t)jb * 128 * ld, ld, v);
+        wave_wait(flags + jb);
+        for (int idx = tid; idx < q * 128; idx += TRSV_THREADS)
+            xs[idx] = __ldcg(X + (int64_t)jb * 128 + (idx & 127) + (int64_t)(idx >> 7) * ldx);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < TRSV_MULTI_QMAX; ++j) {
+            if (j < q) {
+                const double* xj = xs + j * 128 + 32 * h;
+                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+                for (int c = 0; c < 32; c += 4) {
+                    a0 = fma(v[c], xj[c], a0);
+                    a1 = fma(v[c + 1], xj[c + 1], a1);
+                    a2 = fma(v[c + 2], xj[c + 2], a2);
+                    a3 = fma(v[c + 3], xj[c + 3], a3);
+                }
+                red[(j * 4 + h) * 128 + r] = (a0 + a1) + (a2 + a3);
+            }
+        }
+        __syncthreads();
+        if (h == 0) {
+#pragma unroll
+            for (int j = 0; j < TRSV_MULTI_QMAX; ++j)
+                if (j < q) {
+                    const double* rj = red + j * 512 + r;
+                    acc[j] -= (rj[0] + rj[128]) + (rj[256] + rj[384]);
+                }
+        }
+        // (the next step's xs / red writes come after its own wave_wait barrier: no extra barrier needed here)
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < TRSV_MULTI_QMAX; ++j)
+        if (j < q && h == 0) xs[j * 128 + r] = acc[j];
+    mbar_wait(bar, 0);
+    __syncthreads();
+    for (int j = 0; j < q; ++j) {
+        const double sres = tile_apply_smem_512(inv_s, xs + j * 128, red);
+        if (tid < 128) X[row0 + tid + (int64_t)j * ldx] = sres;
+    }
+    wave_publish(flags + i);
+}
+
 // Adjoint: L^T x = b, from the last block.  The CTA with ticket g owns block column i = nb-1-g:
 // x_i = inv_i^T (b_i - sum_{j>i} L[j,i]^T x_j); warp w owns columns 8w .. 8w+7 of a tile, a lane reads rows lane, lane+32,
 // lane+64, lane+96 of each (32 independent loads), then eight shuffle reductions.

@@ -625,3 +625,21 @@ def test_add_samples_failure_leaves_a_refittable_handle():
     assert gp.n_samples == n0
     gp._refit()
     assert np.allclose(gp.predict(X[:5]), m0, rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize("q", [2, 7, 12, 13])
+def test_small_query_batches_use_one_wavefront_solve(q):
+    """q <= 12 takes the latency path (csrc/fgp_api.cu predict_small): ONE multi-right-hand-side wavefront launch; q = 13 is
+    the first batch on the tensor-pipe path.  Same results either way, against the oracle."""
+    F, N, O, make_dataset, make_inputs = _mods()
+    n, d = 1500, 6
+    X, y = make_dataset(0x5EED0030, n, d)
+    Xq = make_inputs(0x5EED0031 + q, q, d)
+    kern, kd = _kern(F, O, "matern2", d)
+    gp = F.GaussianProcess(F.ConstantPrior(0.5), kern, 0.1, None, X, y)
+    ref = O.OracleGaussianProcess(O.ConstantPrior(0.5), kd, 0.1, None, X, y)
+    m, v = gp.predict_mean_variance(Xq)
+    mr, vr = ref.predict_mean_variance(Xq)
+    assert close(m, mr) and close(v, vr)
+    assert close(gp.predict_variance(Xq), ref.predict_variance(Xq))
+    assert gp._h.last_launch_count() <= 12 or q > 12   # one wavefront launch, not one per query
