@@ -9,6 +9,11 @@ namespace fgp {
 template <int KIND, int PMAX>
 struct LmlEpi {
     static constexpr int NV = 2 * PMAX + 1;
+    static constexpr bool HAS_FAST = false;
+    __device__ __forceinline__ bool fast_ok(int64_t, int64_t, int) const { return false; }
+    __device__ __forceinline__ double* fast_base(int64_t, int64_t) const { return nullptr; }
+    __device__ __forceinline__ int fast_ld() const { return 0; }
+    __device__ __forceinline__ double fast_value(double) const { return 0.0; }
     DevKernel k;
     const double* kinv;
     int64_t ld;
@@ -50,6 +55,11 @@ struct LmlEpi {
 
 // sum of Euclidean distances over the strict lower triangle (fit_bandwidth_mean, kernel.rs:94-113)
 struct DistEpi {
+    static constexpr bool HAS_FAST = false;
+    __device__ __forceinline__ bool fast_ok(int64_t, int64_t, int) const { return false; }
+    __device__ __forceinline__ double* fast_base(int64_t, int64_t) const { return nullptr; }
+    __device__ __forceinline__ int fast_ld() const { return 0; }
+    __device__ __forceinline__ double fast_value(double) const { return 0.0; }
     int64_t n;
     double* partial;
     double acc[1];

@@ -103,6 +103,53 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(PairArgs a, const __grid
         for (int mi = 0; mi < 4; ++mi) nrow[mi] = (MODE == PAIR_DOT) ? 0.0 : __ldg(a.na + wr0 + 8 * mi + g);
         double d2v[4][4][2];
         unsigned fix = 0u;  // bit (ni*2+e)*4+mi: the expansion lost > 12 bits for this pair
+        // INTERIOR tiles of a distance-kernel covariance matrix (no diagonal, no padding, nothing above the diagonal): the
+        // per-pair guards (r == c, r < c, r / c beyond the valid extent) and the 64-bit index arithmetic of the general
+        // path below are most of its instructions — here every pair is d2, the repair test, the kernel value and one store
+        // at a 32-bit offset from a per-thread base.  (block-uniform branch)
+        if (MODE == PAIR_D2 && Epi::HAS_FAST && epi.fast_ok(row0, col0, a.symmetric)) {
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double ncol = __ldg(a.nb + wc0 + 8 * ni + 2 * t + e);
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) {
+                        const double nsum = nrow[mi] + ncol;
+                        const double d2 = fmax(fma(-2.0, acc[mi][ni][e], nsum), 0.0);
+                        if (d2 < nsum * 0x1p-12) fix |= 1u << ((ni * 2 + e) * 4 + mi);
+                        d2v[mi][ni][e] = d2;
+                    }
+                }
+            if (fix) {
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+#pragma unroll
+                        for (int mi = 0; mi < 4; ++mi)
+                            if (fix & (1u << ((ni * 2 + e) * 4 + mi))) {
+                                const double* xr = a.xa_c + (wr0 + 8 * mi + g) * dp;
+                                const double* xc = a.xb_c + (wc0 + 8 * ni + 2 * t + e) * dp;
+                                double sdiff = 0.0;
+                                for (int k = 0; k < dp; ++k) {
+                                    const double df = __ldg(xr + k) - __ldg(xc + k);
+                                    sdiff = fma(df, df, sdiff);
+                                }
+                                d2v[mi][ni][e] = sdiff;
+                            }
+            }
+            double* obase = epi.fast_base(wr0 + g, wc0 + 2 * t);
+            const int ldi = epi.fast_ld();
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) obase[8 * mi + (8 * ni + e) * ldi] = epi.fast_value(d2v[mi][ni][e]);
+            epi.finish(row0, col0, active);
+            return;
+        }
         if (MODE != PAIR_DOT) {
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni)
@@ -204,6 +251,19 @@ struct CovWriteEpi {
     // Matern2 c0 = sqrt(5)/|ls|, c1 = |ampl|, c2 = 5/(3 ls^2)
     double c0, c1, c2;
     __device__ __forceinline__ void bind(const CovWriteEpi*) {}
+    // interior-tile fast path of pair_tile_kernel (the two specialised distance kernels only)
+    static constexpr bool HAS_FAST = (KIND == KIND_SQEXP || KIND == KIND_MATERN2);
+    __device__ __forceinline__ bool fast_ok(int64_t row0, int64_t col0, int sym) const {
+        return ld < (int64_t)1 << 24 && row0 + PAIR_TM <= valid_rows && col0 + PAIR_TN <= valid_cols &&
+               (!sym || row0 >= col0 + PAIR_TN);
+    }
+    __device__ __forceinline__ double* fast_base(int64_t r, int64_t c) const { return out + r + c * ld; }
+    __device__ __forceinline__ int fast_ld() const { return (int)ld; }
+    __device__ __forceinline__ double fast_value(double d2) const {
+        if (KIND == KIND_SQEXP) return c1 * exp_nonpos(d2 * c0);
+        const double x = c0 * sqrt(d2);
+        return c1 * (1.0 + x + c2 * d2) * exp_nonpos(-x);
+    }
     __device__ __forceinline__ void operator()(int64_t r, int64_t c, double dot, double d2) const {
         double v;
         if (KIND == KIND_SQEXP) v = c1 * exp_nonpos(d2 * c0);

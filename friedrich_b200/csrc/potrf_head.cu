@@ -152,7 +152,7 @@ __device__ __noinline__ void head_pivot32(double* T, double* rdiag, int s, int l
         HEAD_MARK(34 + 2 * p);
         // rank-8 update of the columns behind the panel, inside the block: tiles (mi, ni), p < ni <= mi <= 3.  All six lower
         // tiles are computed in one straight-line block (fragments first, then 12 independent DMMAs); tiles of finished
-        // columns (ni <= p) keep their old value.  (Nothing is behind the last panel.)
+        // columns (ni <= p) are not stored.  (Nothing is behind the last panel.)
         if (p < 3) {
             double f[3][2], cv[6][2], acc[6][2];
 #pragma unroll
@@ -179,10 +179,11 @@ __device__ __noinline__ void head_pivot32(double* T, double* rdiag, int s, int l
 #pragma unroll
             for (int ni = 1; ni < 4; ++ni)
 #pragma unroll
-                for (int mi = ni; mi < 4; ++mi, ++q) {
-                    Tb[(8 * ni + 2 * t) * S + 8 * mi + g] = (ni > p) ? cv[q][0] - acc[q][0] : cv[q][0];
-                    Tb[(8 * ni + 2 * t + 1) * S + 8 * mi + g] = (ni > p) ? cv[q][1] - acc[q][1] : cv[q][1];
-                }
+                for (int mi = ni; mi < 4; ++mi, ++q)
+                    if (ni > p) {  // (predicated stores: the columns of the panel itself are being read as fragments above)
+                        Tb[(8 * ni + 2 * t) * S + 8 * mi + g] = cv[q][0] - acc[q][0];
+                        Tb[(8 * ni + 2 * t + 1) * S + 8 * mi + g] = cv[q][1] - acc[q][1];
+                    }
         }
         __syncwarp();
         HEAD_MARK(35 + 2 * p);
