@@ -111,6 +111,9 @@ SIGNATURES = {
     "fgp_dbg_gemm_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp]),
     "fgp_dbg_gemm_nt": (C.c_int, [C.c_int, _dp, _i64, _dp, _i64, _dp, _i64, C.c_int, C.c_int, C.c_int, C.c_double,
                                   C.c_int, C.c_int]),
+    "fgp_dbg_ozaki_syrk": (C.c_int, [C.c_int, _dp, _i64, _dp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int]),
+    "fgp_dbg_ozaki_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp]),
 }
 
 _lib = None

@@ -25,6 +25,7 @@
 #include "lml.cuh"
 #include "covariance.cuh"
 #include "sharded.cuh"
+#include "ozaki.cuh"
 
 using namespace fgp;
 
@@ -1378,5 +1379,86 @@ FGP_EXPORT int fgp_dbg_gemm_nt(int device, double* C, int64_t ldc, const double*
     cudaFree(dA);
     cudaFree(dB);
     if (cudaGetLastError() != cudaSuccess) rc = FGP_ERR_CUDA;
+    return rc;
+}
+
+// test hook: C(lower or full, M x M) -= A A^T through the tcgen05 exact-integer path (csrc/ozaki.cu) on device copies of
+// host matrices; A is M x K.  lbo / sbo <= 0: the production descriptor offsets.
+FGP_EXPORT int fgp_dbg_ozaki_syrk(int device, double* C, int64_t ldc, const double* A, int64_t lda, int M, int K, int lower,
+                                  int row_skip, int tiles_per_cta, int lbo, int sbo) {
+    if (M % 128 || K % 128 || M <= 0 || K <= 0 || K > 512) return FGP_ERR_BAD_ARG;
+    DeviceGuard dg(device);
+    if (ozaki_prepare() != cudaSuccess) return FGP_ERR_CUDA;
+    double *dC = nullptr, *dA = nullptr, *dS = nullptr;
+    int8_t* dD = nullptr;
+    int rc = FGP_OK;
+    if (cudaMalloc(&dC, (size_t)M * M * 8) != cudaSuccess || cudaMalloc(&dA, (size_t)M * K * 8) != cudaSuccess ||
+        cudaMalloc(&dS, (size_t)M * 8) != cudaSuccess || cudaMalloc(&dD, ozaki_slice_bytes(M, K)) != cudaSuccess)
+        rc = FGP_ERR_CUDA;
+    if (rc == FGP_OK) {
+        cudaMemcpy2D(dC, (size_t)M * 8, C, (size_t)ldc * 8, (size_t)M * 8, M, cudaMemcpyHostToDevice);
+        cudaMemcpy2D(dA, (size_t)M * 8, A, (size_t)lda * 8, (size_t)M * 8, K, cudaMemcpyHostToDevice);
+        GemmArgs g{};
+        g.C = dC; g.ldc = M;
+        g.M = M; g.N = M; g.K = K;
+        g.alpha = -1.0; g.beta_one = 1; g.lower = lower; g.row_skip = row_skip;
+        ozaki_slice_launch(dA, M, M, K, dD, dS, LaunchCtx{});
+        ozaki_update_launch(g, dD, dS, dD, dS, tiles_per_cta, LaunchCtx{}, lbo > 0 ? (uint32_t)lbo : OZ_LBO, sbo > 0 ? (uint32_t)sbo : OZ_SBO);
+        if (cudaDeviceSynchronize() != cudaSuccess) rc = FGP_ERR_CUDA;
+        cudaMemcpy2D(C, (size_t)ldc * 8, dC, (size_t)M * 8, (size_t)M * 8, M, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(dC);
+    cudaFree(dA);
+    cudaFree(dS);
+    cudaFree(dD);
+    if (cudaGetLastError() != cudaSuccess) rc = FGP_ERR_CUDA;
+    if (gemm_nt_take_error()) rc = FGP_ERR_CUDA;
+    return rc;
+}
+
+// measurement hook: `reps` launches of the slicing kernel and of the tcgen05 update C(lower, M x M) -= A A^T on device-resident
+// random data (A is M x K); CUDA-event time per launch of each
+FGP_EXPORT int fgp_dbg_ozaki_bench(int device, int M, int K, int reps, int tiles_per_cta, double* ms_update, double* ms_slice) {
+    if (M % 128 || K % 128 || M <= 0 || K <= 0 || K > 512 || reps < 1 || !ms_update) return FGP_ERR_BAD_ARG;
+    DeviceGuard dg(device);
+    if (ozaki_prepare() != cudaSuccess) return FGP_ERR_CUDA;
+    double *dC = nullptr, *dA = nullptr, *dS = nullptr;
+    int8_t* dD = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    int rc = FGP_OK;
+    if (cudaMalloc(&dC, (size_t)M * M * 8) != cudaSuccess || cudaMalloc(&dA, (size_t)M * K * 8) != cudaSuccess ||
+        cudaMalloc(&dS, (size_t)M * 8) != cudaSuccess || cudaMalloc(&dD, ozaki_slice_bytes(M, K)) != cudaSuccess ||
+        cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess || cudaEventCreate(&e2) != cudaSuccess)
+        rc = FGP_ERR_CUDA;
+    if (rc == FGP_OK) {
+        fill_random_kernel<<<1024, 256>>>(dC, (int64_t)M * M, 0x9E3779B97F4A7C15ull);
+        fill_random_kernel<<<1024, 256>>>(dA, (int64_t)M * K, 0xD1B54A32D192ED03ull);
+        GemmArgs g{};
+        g.C = dC; g.ldc = M;
+        g.M = M; g.N = M; g.K = K;
+        g.alpha = -1.0; g.beta_one = 1; g.lower = 1;
+        ozaki_slice_launch(dA, M, M, K, dD, dS, LaunchCtx{});
+        ozaki_update_launch(g, dD, dS, dD, dS, tiles_per_cta, LaunchCtx{});
+        cudaEventRecord(e0, nullptr);
+        for (int r = 0; r < reps; ++r) ozaki_slice_launch(dA, M, M, K, dD, dS, LaunchCtx{});
+        cudaEventRecord(e1, nullptr);
+        for (int r = 0; r < reps; ++r) ozaki_update_launch(g, dD, dS, dD, dS, tiles_per_cta, LaunchCtx{});
+        cudaEventRecord(e2, nullptr);
+        if (cudaEventSynchronize(e2) != cudaSuccess) rc = FGP_ERR_CUDA;
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, e0, e1);
+        cudaEventElapsedTime(&b, e1, e2);
+        if (ms_slice) *ms_slice = a / reps;
+        *ms_update = b / reps;
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (e2) cudaEventDestroy(e2);
+    cudaFree(dC);
+    cudaFree(dA);
+    cudaFree(dS);
+    cudaFree(dD);
+    if (cudaGetLastError() != cudaSuccess) rc = FGP_ERR_CUDA;
+    if (gemm_nt_take_error()) rc = FGP_ERR_CUDA;
     return rc;
 }

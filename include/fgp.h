@@ -218,6 +218,14 @@ int64_t fgp_dbg_lower_tiles(int M, int N, int grp, int stride, int* ti_out, int*
  * block is updated by its own launch on the panel stream) */
 int64_t fgp_dbg_lower_tiles_skip(int M, int N, int grp, int stride, int row_skip, int* ti_out, int* tj_out, int64_t capacity);
 
+/* test hook: C (M x M, lower != 0: tiles on/below the diagonal, the first row_skip tile rows left out) -= A A^T, A is M x K
+ * (K = 128..512), through the tcgen05 / TMEM exact-integer trailing update (csrc/ozaki.cu) on device copies of host
+ * matrices; tiles_per_cta, lbo, sbo <= 0: production values */
+int fgp_dbg_ozaki_syrk(int device, double* C, int64_t ldc, const double* A, int64_t lda, int M, int K, int lower, int row_skip,
+                       int tiles_per_cta, int lbo, int sbo);
+/* measurement hook: CUDA-event time per launch of the digit slicing kernel and of the tcgen05 update on random device data */
+int fgp_dbg_ozaki_bench(int device, int M, int K, int reps, int tiles_per_cta, double* ms_update, double* ms_slice);
+
 #ifdef __cplusplus
 }
 #endif
