@@ -113,6 +113,7 @@ SIGNATURES = {
                                   C.c_int, C.c_int]),
     "fgp_dbg_ozaki_syrk": (C.c_int, [C.c_int, _dp, _i64, _dp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int]),
+    "fgp_dbg_ozaki_experiment": (None, [C.c_int]),
     "fgp_dbg_ozaki_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp]),
 }
 

@@ -1418,6 +1418,8 @@ FGP_EXPORT int fgp_dbg_ozaki_syrk(int device, double* C, int64_t ldc, const doub
 
 // measurement hook: `reps` launches of the slicing kernel and of the tcgen05 update C(lower, M x M) -= A A^T on device-resident
 // random data (A is M x K); CUDA-event time per launch of each
+FGP_EXPORT void fgp_dbg_ozaki_experiment(int flags) { ozaki_set_experiment(flags); }
+
 FGP_EXPORT int fgp_dbg_ozaki_bench(int device, int M, int K, int reps, int tiles_per_cta, double* ms_update, double* ms_slice) {
     if (M % 128 || K % 128 || M <= 0 || K <= 0 || K > 512 || reps < 1 || !ms_update) return FGP_ERR_BAD_ARG;
     DeviceGuard dg(device);

@@ -72,6 +72,7 @@ struct OzArgs {
     int KS;          // k-steps (K / 32)
     int tiles, tpc;  // tiles of the launch, tiles per CTA (CTA b: tiles [b * tpc, (b + 1) * tpc))
     uint32_t lbo, sbo;
+    int exp;         // measurement switches (tools/ozaki_check.py): 1 = no epilogue arithmetic / stores, 2 = no operand copies, 4 = no MMAs
 };
 
 // mbarrier wait with a watchdog: a protocol error traps instead of hanging the device
@@ -115,28 +116,52 @@ __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_
 __device__ __forceinline__ uint64_t oz_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
 }
+__device__ __forceinline__ void tma_wait_group_all0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
-__device__ __forceinline__ void tma_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
 
 // kind::i8, D = S32, A = B = signed 8 bit, both K-major, N = 128, M = 128
 constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+// the MMAs of one k-step of pass PASS (groups 4 PASS .. 4 PASS + 3), fully unrolled: the descriptors differ from the stage's
+// base descriptors by compile-time constants (slice i sits i * 4096 bytes = i * 256 descriptor units into its part)
+template <int PASS>
+__device__ __forceinline__ void issue_kstep(uint32_t tmem_base, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t not_first) {
+#pragma unroll
+    for (int gg = 0; gg < 4; ++gg) {
+        constexpr int G0 = PASS * 4;
+#pragma unroll
+        for (int i = 0; i <= G0 + gg; ++i) {
+            const int j = G0 + gg - i;
+            umma_i8(tmem_base + gg * 128, desc64(a_lo + i * (OZ_BLOCK_BYTES >> 4), hi), desc64(b_lo + j * (OZ_BLOCK_BYTES >> 4), hi), OZ_IDESC,
+                    i > 0 ? 1u : not_first);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_update_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ CUtensorMap tmC, const OzArgs o) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* ring = smem;
-    double* staging = reinterpret_cast<double*>(smem + OZ_STAGES * OZ_STAGE_BYTES);
     unsigned char* tail = smem + OZ_STAGES * OZ_STAGE_BYTES + OZ_STAGING_BYTES;
-    double* colsc = reinterpret_cast<double*>(tail);                    // 128 doubles
-    uint64_t* full = reinterpret_cast<uint64_t*>(tail + 1024);          // [OZ_STAGES]
+    uint64_t* full = reinterpret_cast<uint64_t*>(tail);                 // [OZ_STAGES]
     uint64_t* empty = full + OZ_STAGES;                                 // [OZ_STAGES]
     uint64_t* tmem_full = empty + OZ_STAGES;
     uint64_t* tmem_empty = tmem_full + 1;
@@ -151,7 +176,7 @@ ozaki_update_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ 
             mbar_init(&empty[s], 1);
         }
         mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 4);
+        mbar_init(tmem_empty, OZ_EPI_WARPS);
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -164,111 +189,132 @@ ozaki_update_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        // ===== producer: bulk copies of the digit blocks =====
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = t_begin; t < t_end; ++t) {
-                int ti, tj;
-                gemm_tile_decode(g, t, ti, tj);
-                const int8_t* a0 = o.SA + (int64_t)ti * o.KS * OZ_PART_BYTES;
-                const int8_t* b0 = o.SB + (int64_t)tj * o.KS * OZ_PART_BYTES;
-                for (int pass = 0; pass < 2; ++pass) {
-                    const uint32_t bytes = pass == 0 ? OZ_PART_BYTES / 2 : OZ_PART_BYTES;
-                    for (int ks = 0; ks < o.KS; ++ks) {
-                        oz_wait(&empty[stage], phase ^ 1);
+        // ===== producer: bulk copies of the digit blocks (the whole warp walks the loop, one elected lane issues) =====
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+            int ti, tj;
+            gemm_tile_decode(g, t, ti, tj);
+            const int8_t* a0 = o.SA + (int64_t)ti * o.KS * OZ_PART_BYTES;
+            const int8_t* b0 = o.SB + (int64_t)tj * o.KS * OZ_PART_BYTES;
+            for (int pass = 0; pass < 2; ++pass) {
+                const uint32_t bytes = pass == 0 ? OZ_PART_BYTES / 2 : OZ_PART_BYTES;
+                for (int ks = 0; ks < o.KS; ++ks) {
+                    oz_wait(&empty[stage], phase ^ 1);
+                    if (elect_one()) {
                         unsigned char* dst = ring + stage * OZ_STAGE_BYTES;
-                        mbar_arrive_expect_tx(&full[stage], 2 * bytes);
-                        tma_load_1d(dst, a0 + (int64_t)ks * OZ_PART_BYTES, bytes, &full[stage]);
-                        tma_load_1d(dst + OZ_PART_BYTES, b0 + (int64_t)ks * OZ_PART_BYTES, bytes, &full[stage]);
-                        if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
+                        if (o.exp & 2) {
+                            mbar_arrive(&full[stage]);
+                        } else {
+                            mbar_arrive_expect_tx(&full[stage], 2 * bytes);
+                            tma_load_1d(dst, a0 + (int64_t)ks * OZ_PART_BYTES, bytes, &full[stage]);
+                            tma_load_1d(dst + OZ_PART_BYTES, b0 + (int64_t)ks * OZ_PART_BYTES, bytes, &full[stage]);
+                        }
                     }
+                    __syncwarp();
+                    if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0, npass = 0;
-            for (int t = t_begin; t < t_end; ++t) {
-                for (int pass = 0; pass < 2; ++pass, ++npass) {
-                    oz_wait(tmem_empty, (npass & 1) ^ 1);   // the epilogue has drained the four accumulators
+        // ===== MMA issuer: the whole warp walks the loop (uniform control flow and descriptor arithmetic), one elected lane
+        // issues the tcgen05.mma / tcgen05.commit instructions =====
+        int stage = 0;
+        uint32_t phase = 0, npass = 0;
+        const uint32_t hi = (uint32_t)(oz_desc(0, o.lbo, o.sbo) >> 32), lbo_field = (o.lbo >> 4) << 16;
+        const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFFu) >> 4) | lbo_field;
+        for (int t = t_begin; t < t_end; ++t) {
+            for (int pass = 0; pass < 2; ++pass, ++npass) {
+                oz_wait(tmem_empty, (npass & 1) ^ 1);   // the epilogue has drained the four accumulators
+                tc_fence_after();
+                for (int ks = 0; ks < o.KS; ++ks) {
+                    oz_wait(&full[stage], phase);
                     tc_fence_after();
-                    const int g0 = pass * 4;
-                    for (int ks = 0; ks < o.KS; ++ks) {
-                        oz_wait(&full[stage], phase);
-                        tc_fence_after();
-                        const uint32_t sa = smem_u32(ring + stage * OZ_STAGE_BYTES), sb = sa + OZ_PART_BYTES;
-                        for (int gg = 0; gg < 4; ++gg) {
-                            const int grp = g0 + gg;
-                            const uint32_t d = tmem_base + gg * 128;
-                            for (int i = 0; i <= grp; ++i) {
-                                const int j = grp - i;
-                                umma_i8(d, oz_desc(sa + i * OZ_BLOCK_BYTES, o.lbo, o.sbo), oz_desc(sb + j * OZ_BLOCK_BYTES, o.lbo, o.sbo),
-                                        OZ_IDESC, (ks > 0 || i > 0) ? 1u : 0u);
-                            }
+                    if (elect_one()) {
+                        const uint32_t a_lo = ring_lo + stage * (OZ_STAGE_BYTES >> 4), b_lo = a_lo + (OZ_PART_BYTES >> 4);
+                        if (!(o.exp & 4)) {
+                            if (pass == 0) issue_kstep<0>(tmem_base, a_lo, b_lo, hi, ks > 0);
+                            else issue_kstep<1>(tmem_base, a_lo, b_lo, hi, ks > 0);
                         }
-                        tc_commit(&empty[stage]);   // the stage is free once these MMAs have read it
-                        if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
+                        tc_commit(&empty[stage]);                    // the stage is free once these MMAs have read it
+                        if (ks == o.KS - 1) tc_commit(tmem_full);    // accumulators complete
                     }
-                    tc_commit(tmem_full);           // accumulators complete
+                    __syncwarp();
+                    if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else {
-        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-        const int quarter = warp & 3, row = quarter * 32 + lane;
-        const int etid = (warp - 2) * 32 + lane;
+        // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4 (32 tile rows), column half = (warp - 2) / 4 =====
+        const int quarter = warp & 3, row = quarter * 32 + lane, half = (warp - 2) >> 2;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        uint32_t npass = 0, nchunk = 0;
+        double* stg = reinterpret_cast<double*>(smem + OZ_STAGES * OZ_STAGE_BYTES) + (warp - 2) * (32 * 16);   // this warp's 4 KB image
+        uint32_t npass = 0;
         for (int t = t_begin; t < t_end; ++t) {
             int ti, tj;
             gemm_tile_decode(g, t, ti, tj);
             const bool diag = g.lower && ti == tj;
             const int m0 = ti * 128, n0 = tj * 128;
-            colsc[etid] = o.scB[n0 + etid];
             const double rs = o.scA[m0 + row];
-            epi_bar();
             for (int pass = 0; pass < 2; ++pass, ++npass) {
                 // pass 0 carries the groups 0..3: weight 128^4 = 2^28 over pass 1; alpha = -1; sc = 2^(e-30): 2^(e_r+e_c-61) = rs*cs/2
                 const double rf = rs * (pass == 0 ? -134217728.0 : -0.5);
                 oz_wait(tmem_full, npass & 1);
                 tc_fence_after();
-                for (int ch = 0; ch < 128 / OZ_STAGING_COLS; ++ch, ++nchunk) {
-                    int v[4][16];
+                // phase 1 (TMEM busy, the MMA warp waits): the warp's 32 rows x 64 columns of the four accumulators -> one exact f64
+                // per element in registers.  Conversions to f64 run at 16 / clk / SM, so the integers are combined pairwise in 64-bit
+                // integer arithmetic and turned into doubles by the 2^52 trick (exact for |u| < 2^51): 3 f64 operations per element
+                double x[64];
 #pragma unroll
-                    for (int gg = 0; gg < 4; ++gg) tmem_ld16(lane_addr + gg * 128 + ch * OZ_STAGING_COLS, v[gg]);
+                for (int ch = 0; ch < 8; ++ch) {
+                    int v[4][8];
+#pragma unroll
+                    for (int gg = 0; gg < 4; ++gg) tmem_ld8(lane_addr + gg * 128 + half * 64 + ch * 8, v[gg]);
                     tmem_ld_wait();
-                    if (ch == 128 / OZ_STAGING_COLS - 1) {   // TMEM is free for the next pass as soon as the last load has landed
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(tmem_empty);
-                    }
-                    double* st = staging + (nchunk & 1) * (128 * OZ_STAGING_COLS) + row;
 #pragma unroll
-                    for (int c = 0; c < OZ_STAGING_COLS; ++c) {
-                        const long long s = (long long)v[0][c] * 2097152ll + (long long)v[1][c] * 16384ll + (long long)v[2][c] * 128ll + (long long)v[3][c];
-                        const int cl = ch * OZ_STAGING_COLS + c;
-                        const double val = (double)s * (rf * colsc[cl]);
-                        st[c * 128] = (diag && row < cl) ? 0.0 : val;
+                    for (int c = 0; c < 8; ++c) {
+                        const long long u = (long long)v[0][c] * 128 + v[1][c], w = (long long)v[2][c] * 128 + v[3][c];
+                        const double du = __longlong_as_double(u + 0x4338000000000000ll) - 6755399441055744.0;
+                        const double dw = __longlong_as_double(w + 0x4338000000000000ll) - 6755399441055744.0;
+                        x[ch * 8 + c] = fma(du, 16384.0, dw);   // exact: < 2^47
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty);   // TMEM is free: the next pass's MMAs run under phase 2
+                if (o.exp & 1) {
+                    double sum = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 64; ++c) sum += x[c];
+                    if (sum == 12345.678) g.C[0] = sum;   // keep phase 1 observable
+                    continue;
+                }
+                // phase 2: x * (row scale * column scale) leaves through the warp's own 32 x 16 staging image, 16 columns at a time,
+                // as TMA reduce-adds into C (f64 add at the L2; the SM never reads C).  The two passes' additions to an element
+                // are applied in a fixed order: pass 0's reduces have been PERFORMED before pass 1 issues its first.
+                if (lane == 0) {
+                    if (pass == 1) tma_wait_group_all0();
+                }
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) {
+                    const int c0 = half * 64 + cb * 16;
+                    if (lane == 0) tma_wait_group_read0();   // the previous image has been read
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const double val = x[cb * 16 + c] * (rf * __ldg(o.scB + n0 + c0 + c));
+                        stg[c * 32 + lane] = (diag && row < c0 + c) ? 0.0 : val;
                     }
                     fence_proxy_async_smem();
-                    if (etid == 0) {
-                        // every earlier reduce has read its staging image; at the first chunk of a pass also: has been PERFORMED,
-                        // so that the two passes' additions to an element of C are applied in a fixed order
-                        if (ch == 0) tma_wait_group0();
-                        else tma_wait_group_read0();
-                    }
-                    epi_bar();
-                    if (etid == 0) {
-                        tma_reduce_add_2d(&tmC, m0, n0 + ch * OZ_STAGING_COLS, staging + (nchunk & 1) * (128 * OZ_STAGING_COLS));
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_reduce_add_2d(&tmC, m0 + quarter * 32, n0 + c0, stg);
                         tma_commit_group();
                     }
                 }
             }
         }
-        if (etid == 0) tma_wait_group0();
+        if (lane == 0) tma_wait_group_all0();
     }
 
     tc_fence_before();
@@ -296,6 +342,9 @@ void ozaki_slice_launch(const double* P, int64_t ld, int64_t rows, int K, int8_t
     ozaki_slice_kernel<<<(unsigned)(rows / 128), 512, 0, ctx.st>>>(P, ld, K, digits, scale);
 }
 
+static int g_oz_exp = 0;
+void ozaki_set_experiment(int flags) { g_oz_exp = flags; }
+
 int64_t ozaki_update_launch(const GemmArgs& g, const int8_t* digitsA, const double* scaleA, const int8_t* digitsB,
                             const double* scaleB, int tiles_per_cta, const LaunchCtx& ctx, uint32_t lbo, uint32_t sbo) {
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
@@ -309,7 +358,7 @@ int64_t ozaki_update_launch(const GemmArgs& g, const int8_t* digitsA, const doub
     gemm_nt_plan(p);
     alignas(64) CUtensorMap tmC;
     const int64_t ncols = g.lower ? g.M : g.N;
-    if (!make_tile_map(&tmC, g.C, g.M, ncols, g.ldc, 128, OZ_STAGING_COLS)) {
+    if (!make_tile_map(&tmC, g.C, g.M, ncols, g.ldc, 32, 16)) {
         gemm_nt_flag_error();
         return 0;
     }
@@ -322,6 +371,7 @@ int64_t ozaki_update_launch(const GemmArgs& g, const int8_t* digitsA, const doub
     if (tpc <= 0) tpc = (int)std::max<int64_t>(1, std::min<int64_t>(4, tiles / (2 * num_sms)));
     o.tpc = tpc;
     o.lbo = lbo; o.sbo = sbo;
+    o.exp = g_oz_exp;
     const unsigned grid = (unsigned)((tiles + tpc - 1) / tpc);
     ProfScope ps(ctx, PROF_GEMM, gemm_nt_flops(g));
     ozaki_update_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, ctx.st>>>(p, tmC, o);

@@ -14,9 +14,9 @@
 // max_row * max_col per term — the size of the rounding of one f64 multiply-add.  The 36 kept products are grouped by
 // g = i + j (equal weight 128^(14-g)): one accumulator per group, four groups per pass through K (TMEM holds four
 // 128x128 int32 accumulators), two passes per tile: g = 0..3 (10 products) and g = 4..7 (26 products).  After each pass
-// the four accumulators are combined in exact 64-bit integer arithmetic, converted to f64 (exact: < 2^47), scaled by the
-// row / column powers of two (exact) and added to C by TMA reduce-adds (f64 add at the L2) — two roundings per element
-// and launch, against 512 in the f64 DMMA kernel.
+// the four accumulators are combined exactly (64-bit integers, then f64: every partial sum < 2^47), scaled by the row /
+// column powers of two (exact) and added to C by TMA reduce-adds (f64 add at the L2) — two roundings per element and
+// launch, against 512 in the f64 DMMA kernel.
 //
 // Data layout.  `ozaki_slice_launch` writes the digits in the order the tensor core reads them, so the GEMM kernel moves
 // them with 1-D bulk copies and no swizzle: for row tile T (128 rows), k-step s (32 contraction bytes = one tcgen05.mma) and
@@ -26,9 +26,11 @@
 // (between 8-row groups) is 128.  One stage of the operand ring is the 8 slices of the tile's row block (32 KB) and of its
 // column block (32 KB) for one k-step; pass 0 only fetches slices 0..3 of each.
 //
-// Kernel roles (192 threads, one CTA per SM): warp 0 = TMEM allocation + one lane issuing the bulk copies, warp 1 = one
-// lane issuing the MMAs (36 x K/32 per tile) and the commits that release stages / publish accumulators, warps 2..5 =
-// epilogue (tcgen05.ld of the warp's 32 TMEM lanes = 32 tile rows, combine, stage 16 columns, TMA reduce-add).
+// Kernel roles (320 threads, one CTA per SM): warp 0 = TMEM allocation + the bulk copies, warp 1 = the MMAs (36 x K/32 per
+// tile) and the commits that release stages / publish accumulators — both warps walk their loops as a whole (uniform
+// control flow and descriptor arithmetic) and one elected lane issues; warps 2..9 = epilogue: tcgen05.ld of the warp's 32
+// TMEM lanes (= 32 tile rows) x 64 columns into registers (one exact f64 per element), release of the accumulators, then
+// scaling and TMA reduce-adds into C from the warp's own 32 x 16 staging image while the next pass's MMAs already run.
 #pragma once
 
 #include "gemm_nt.cuh"
@@ -41,16 +43,17 @@ constexpr int OZ_BLOCK_BYTES = 128 * OZ_KSTEP;        // one slice of one row ti
 constexpr int OZ_STAGES = 3;
 constexpr int OZ_PART_BYTES = OZ_SLICES * OZ_BLOCK_BYTES;                 // 32 KB: row (or column) block of one stage
 constexpr int OZ_STAGE_BYTES = 2 * OZ_PART_BYTES;                          // 64 KB
-constexpr int OZ_STAGING_COLS = 16;
-constexpr int OZ_STAGING_BYTES = 2 * 128 * OZ_STAGING_COLS * 8;            // two 128 x 16 f64 images
-constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + OZ_STAGING_BYTES + 2048;
-constexpr int OZ_THREADS = 192;
+constexpr int OZ_EPI_WARPS = 8;
+constexpr int OZ_STAGING_BYTES = OZ_EPI_WARPS * 32 * 16 * 8;               // one 32 x 16 f64 image per epilogue warp
+constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + OZ_STAGING_BYTES + 1024;
+constexpr int OZ_THREADS = 32 * (2 + OZ_EPI_WARPS);
 constexpr uint32_t OZ_LBO = 2048, OZ_SBO = 128;
 
 // bytes of the digit blob / doubles of the scale vector of a rows x K panel (rows % 128 == 0, K % 32 == 0)
 inline size_t ozaki_slice_bytes(int64_t rows, int K) { return (size_t)rows * (size_t)K * OZ_SLICES; }
 
 cudaError_t ozaki_prepare();
+void ozaki_set_experiment(int flags);  // measurement switches of the update kernel (0 = production)
 // digits + row scales (2^(e_r - 30), 0 for an all-zero row, NaN when the row holds a non-finite value) of P (column-major, ld)
 void ozaki_slice_launch(const double* P, int64_t ld, int64_t rows, int K, int8_t* digits, double* scale, const LaunchCtx& ctx);
 // C -= P P^T on the tiles GemmArgs describes (C, ldc, M, N, lower, row_skip, grp, stride, K; alpha = -1, beta = 1 implied);

@@ -224,6 +224,8 @@ int64_t fgp_dbg_lower_tiles_skip(int M, int N, int grp, int stride, int row_skip
 int fgp_dbg_ozaki_syrk(int device, double* C, int64_t ldc, const double* A, int64_t lda, int M, int K, int lower, int row_skip,
                        int tiles_per_cta, int lbo, int sbo);
 /* measurement hook: CUDA-event time per launch of the digit slicing kernel and of the tcgen05 update on random device data */
+/* measurement switches of the update kernel: 1 = no epilogue arithmetic / stores, 2 = no operand copies, 4 = no MMAs; 0 = production */
+void fgp_dbg_ozaki_experiment(int flags);
 int fgp_dbg_ozaki_bench(int device, int M, int K, int reps, int tiles_per_cta, double* ms_update, double* ms_slice);
 
 #ifdef __cplusplus

@@ -79,7 +79,7 @@ def check():
 
 def bench():
     for (M, K) in [(15872, 512), (8192, 512), (4096, 512), (2048, 512), (32256, 512), (15872, 256)]:
-        for tpc in (1, 2, 4, 8):
+        for tpc in (2, 4):
             mu, msl = C.c_double(0), C.c_double(0)
             rc = lib.fgp_dbg_ozaki_bench(0, M, K, 5, tpc, C.byref(mu), C.byref(msl))
             tiles = (M // 128) * (M // 128 + 1) // 2
@@ -92,6 +92,17 @@ def bench():
                               "speedup_vs_dmma": md.value / mu.value if mu.value else None}), flush=True)
 
 
+def experiments():
+    """which part bounds the update kernel: the same launch with parts switched off"""
+    for flags, what in [(0, "production"), (1, "no epilogue"), (2, "no operand copies"), (3, "MMAs only"), (4, "no MMAs"),
+                        (5, "copies only"), (6, "epilogue only"), (11, "MMAs only, N=256 probe (18 per k-step)")]:
+        lib.fgp_dbg_ozaki_experiment(flags)
+        mu = C.c_double(0)
+        rc = lib.fgp_dbg_ozaki_bench(0, 15872, 512, 3, 2, C.byref(mu), None)
+        print(json.dumps({"experiment": what, "flags": flags, "rc": rc, "update_ms": mu.value, "us_per_tile": mu.value * 148 / 7750 * 1e3}), flush=True)
+    lib.fgp_dbg_ozaki_experiment(0)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     good = True
@@ -100,3 +111,5 @@ if __name__ == "__main__":
         print("CHECK", "OK" if good else "FAILED", flush=True)
     if what in ("bench", "all") and good:
         bench()
+    if what == "exp":
+        experiments()
