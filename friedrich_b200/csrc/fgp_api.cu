@@ -106,6 +106,13 @@ int prepare_head_work(fgp_model* m, int64_t jb_begin, PotrfWork* w, int64_t* p0)
     }
     *w = PotrfWork{m->inv.p, m->invT.p, m->Wp.p, m->Pscr.p, m->head_sync, {m->pbuf[0].p, m->pbuf[1].p}, m->evTop, m->evRest,
                    {m->evCopy[0], m->evCopy[1]}};
+    if (m->tcgen05) {   // 8 digit bytes per panel element = as many bytes as the f64 panel buffer
+        CU(m, m->ozDigits.reserve((size_t)m->cap * HEAD_PANEL));
+        CU(m, m->ozScale.reserve((size_t)m->cap));
+        if (ozaki_prepare() != cudaSuccess) return fail(m, FGP_ERR_CUDA, "tcgen05 update kernel could not be configured");
+        w->oz_digits = reinterpret_cast<int8_t*>(m->ozDigits.p);
+        w->oz_scale = m->ozScale.p;
+    }
     return FGP_OK;
 }
 
@@ -460,6 +467,7 @@ FGP_EXPORT int fgp_set_option(fgp_model* m, int option, int64_t value) {
     switch (option) {
         case FGP_OPT_LOOKAHEAD: m->lookahead = value != 0; return FGP_OK;
         case FGP_OPT_HEAD: m->head_schedule = value != 0; return FGP_OK;
+        case FGP_OPT_TCGEN05: m->tcgen05 = value != 0; return FGP_OK;
         default: return fail(m, FGP_ERR_BAD_ARG, "unknown option");
     }
 }

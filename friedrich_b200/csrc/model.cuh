@@ -70,6 +70,8 @@ struct fgp_model {
     fgp::DevBuf L, inv, invT;              // factor [cap x cap], inverse diagonal blocks and their transposes
     // head schedule of the blocked Cholesky (potrf.cuh PotrfWork): per-panel inverse blocks W, head scratch, panel buffers
     fgp::DevBuf Wp, Pscr, pbuf[2];
+    fgp::DevBuf ozDigits, ozScale;         // base-128 digit slices + row scales of the panel being applied (csrc/ozaki.cuh)
+    bool tcgen05 = true;                   // FGP_OPT_TCGEN05
     int* head_sync = nullptr;              // [head_sync_cap][HEAD_SYNC_INTS]
     int64_t head_sync_cap = 0;
     std::vector<int64_t> pstart;           // first block column of every panel of the current factor (W slot = index)

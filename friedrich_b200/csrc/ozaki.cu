@@ -9,19 +9,19 @@ namespace fgp {
 namespace {
 
 // ------------------------------------------------------------------------------------------------------------------
-// slicing: one CTA per row tile (128 rows), 512 threads = 4 k-quarters x 128 rows
-__global__ void __launch_bounds__(512) ozaki_slice_kernel(const double* __restrict__ P, int64_t ld, int K, int8_t* __restrict__ digits,
-                                                          double* __restrict__ scale) {
-    __shared__ double red[4][128];
+// slicing, step 1: row scales.  One CTA per row tile (128 rows), 1024 threads = 8 k-groups x 128 rows (coalesced along rows).
+__global__ void __launch_bounds__(1024) ozaki_rowmax_kernel(const double* __restrict__ P, int64_t ld, int K, double* __restrict__ scale) {
+    __shared__ double red[8][128];
     __shared__ int bad[128];
     const int r = threadIdx.x & 127, q = threadIdx.x >> 7;
     const int64_t T = blockIdx.x;
-    const int kq = K >> 2, k0 = q * kq, KS = K / OZ_KSTEP;
-    const double* p = P + T * 128 + r + (int64_t)k0 * ld;
+    const int kq = K >> 3;
+    const double* p = P + T * 128 + r + (int64_t)(q * kq) * ld;
     if (q == 0) bad[r] = 0;
     __syncthreads();
     double m = 0.0;
     bool nonfinite = false;
+#pragma unroll 8
     for (int k = 0; k < kq; ++k) {
         const double a = fabs(p[(int64_t)k * ld]);
         nonfinite |= !(a <= 1.7976931348623157e308);
@@ -30,37 +30,48 @@ __global__ void __launch_bounds__(512) ozaki_slice_kernel(const double* __restri
     red[q][r] = m;
     if (nonfinite) bad[r] = 1;
     __syncthreads();
-    m = fmax(fmax(red[0][r], red[1][r]), fmax(red[2][r], red[3][r]));
-    // max |p| < 2^e
-    int e = ((__double2hiint(m) >> 20) & 0x7ff) - 1022;
-    const bool zero = (m == 0.0) || e < -900;
-    const bool nan = bad[r] || e > 900;
-    if (q == 0) scale[T * 128 + r] = nan ? __longlong_as_double(0x7ff8000000000000ll) : zero ? 0.0 : __hiloint2double((1023 + e - 30) << 20, 0);
-    const double up = (zero || nan) ? 0.0 : __hiloint2double((1023 + 55 - e) << 20, 0);  // 2^(55 - e)
-    for (int s = k0 / OZ_KSTEP; s < (k0 + kq) / OZ_KSTEP; ++s) {
-#pragma unroll 1
-        for (int kh = 0; kh < 2; ++kh) {
-            uint32_t w[OZ_SLICES][4];
+    if (q == 0) {
 #pragma unroll
-            for (int i = 0; i < OZ_SLICES; ++i) w[i][0] = w[i][1] = w[i][2] = w[i][3] = 0u;
-            const double* src = P + T * 128 + r + (int64_t)(s * OZ_KSTEP + kh * 16) * ld;
-#pragma unroll
-            for (int kb = 0; kb < 16; ++kb) {
-                long long X = __double2ll_rn(src[(int64_t)kb * ld] * up);
-#pragma unroll
-                for (int i = OZ_SLICES - 1; i >= 1; --i) {
-                    const int d = (((int)X & 127) ^ 64) - 64;   // balanced digit in [-64, 63]
-                    X = (X - d) >> 7;
-                    w[i][kb >> 2] |= (uint32_t)(d & 0xff) << (8 * (kb & 3));
-                }
-                w[0][kb >> 2] |= (uint32_t)((int)X & 0xff) << (8 * (kb & 3));   // |top digit| <= 65
-            }
-            int8_t* dst = digits + ((T * KS + s) * OZ_SLICES) * (int64_t)OZ_BLOCK_BYTES + kh * 2048 + (r >> 3) * 128 + (r & 7) * 16;
-#pragma unroll
-            for (int i = 0; i < OZ_SLICES; ++i)
-                *reinterpret_cast<uint4*>(dst + (int64_t)i * OZ_BLOCK_BYTES) = make_uint4(w[i][0], w[i][1], w[i][2], w[i][3]);
-        }
+        for (int i = 1; i < 8; ++i) m = fmax(m, red[i][r]);
+        const int e = ((__double2hiint(m) >> 20) & 0x7ff) - 1022;   // max |p| < 2^e
+        const bool zero = (m == 0.0) || e < -900;
+        const bool nan = bad[r] || e > 900;
+        scale[T * 128 + r] = nan ? __longlong_as_double(0x7ff8000000000000ll) : zero ? 0.0 : __hiloint2double((1023 + e - 30) << 20, 0);
     }
+}
+
+// slicing, step 2: digits.  CTA (T, s) = row tile T, k-step s; 256 threads = 2 k-halves x 128 rows; every thread turns 16
+// consecutive k of its row into 8 x 16 digit bytes (one 16-byte store per slice, coalesced across the rows of a warp).
+__global__ void __launch_bounds__(256) ozaki_digits_kernel(const double* __restrict__ P, int64_t ld, int KS, const double* __restrict__ scale,
+                                                           int8_t* __restrict__ digits) {
+    const int r = threadIdx.x & 127, kh = threadIdx.x >> 7;
+    const int64_t T = blockIdx.x;
+    const int s = blockIdx.y;
+    const double sc = scale[T * 128 + r];
+    // scale = 2^(e - 30): digits are taken from rint(p * 2^(55 - e)) = rint(p * 2^25 / scale)
+    const double up = (sc > 0.0) ? __hiloint2double(((2046 + 25) << 20) - __double2hiint(sc), 0) : 0.0;   // hi word of 2^x = (1023 + x) << 20
+    const double* src = P + T * 128 + r + (int64_t)(s * OZ_KSTEP + kh * 16) * ld;
+    double a[16];
+#pragma unroll
+    for (int kb = 0; kb < 16; ++kb) a[kb] = src[(int64_t)kb * ld];
+    uint32_t w[OZ_SLICES][4];
+#pragma unroll
+    for (int i = 0; i < OZ_SLICES; ++i) w[i][0] = w[i][1] = w[i][2] = w[i][3] = 0u;
+#pragma unroll
+    for (int kb = 0; kb < 16; ++kb) {
+        long long X = __double2ll_rn(a[kb] * up);
+#pragma unroll
+        for (int i = OZ_SLICES - 1; i >= 1; --i) {
+            const int d = (((int)X & 127) ^ 64) - 64;   // balanced digit in [-64, 63]
+            X = (X - d) >> 7;
+            w[i][kb >> 2] |= (uint32_t)(d & 0xff) << (8 * (kb & 3));
+        }
+        w[0][kb >> 2] |= (uint32_t)((int)X & 0xff) << (8 * (kb & 3));   // |top digit| <= 65
+    }
+    int8_t* dst = digits + ((T * KS + s) * OZ_SLICES) * (int64_t)OZ_BLOCK_BYTES + kh * 2048 + (r >> 3) * 128 + (r & 7) * 16;
+#pragma unroll
+    for (int i = 0; i < OZ_SLICES; ++i)
+        *reinterpret_cast<uint4*>(dst + (int64_t)i * OZ_BLOCK_BYTES) = make_uint4(w[i][0], w[i][1], w[i][2], w[i][3]);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -339,7 +350,8 @@ cudaError_t ozaki_prepare() {
 void ozaki_slice_launch(const double* P, int64_t ld, int64_t rows, int K, int8_t* digits, double* scale, const LaunchCtx& ctx) {
     if (rows <= 0 || K <= 0) return;
     ProfScope ps(ctx, PROF_OTHER, 0.0);
-    ozaki_slice_kernel<<<(unsigned)(rows / 128), 512, 0, ctx.st>>>(P, ld, K, digits, scale);
+    ozaki_rowmax_kernel<<<(unsigned)(rows / 128), 1024, 0, ctx.st>>>(P, ld, K, scale);
+    ozaki_digits_kernel<<<dim3((unsigned)(rows / 128), (unsigned)(K / OZ_KSTEP)), 256, 0, ctx.st>>>(P, ld, K / OZ_KSTEP, scale, digits);
 }
 
 static int g_oz_exp = 0;

@@ -1,5 +1,6 @@
 // potrf.cu — diagonal-tile factorisation kernel and the blocked lower Cholesky driver (contract in potrf.cuh).
 #include "potrf.cuh"
+#include "ozaki.cuh"
 
 namespace fgp {
 
@@ -517,6 +518,22 @@ int64_t potrf_lower_head(double* A, int64_t lda, int64_t np, int64_t jb_begin, c
         g.alpha = -1.0; g.beta_one = 1; g.lower = 1; g.row_skip = (int)skip;
         cnt->launches += gemm_nt_launch(g, c) > 0;
     };
+    // the same update (skip > 0: everything but the first `skip` tile rows) on tcgen05 when enough rows are left: digit slices
+    // of the whole solved panel, then exact int8 products (csrc/ozaki.cuh)
+    auto update_big = [&](int64_t J, int64_t Jend, int64_t p, int64_t skip, const LaunchCtx& c) {
+        const int64_t rows = np - Jend * TILE;
+        if (!w.oz_digits || rows < OZ_MIN_ROWS) {
+            update(J, Jend, p, 0, skip, c);
+            return;
+        }
+        const int K = (int)((Jend - J) * TILE);
+        ozaki_slice_launch(w.pbuf[p & 1], rows, rows, K, w.oz_digits, w.oz_scale, c);
+        GemmArgs g{};
+        g.C = A + Jend * TILE * (lda + 1); g.ldc = lda;
+        g.M = (int)rows; g.N = g.M; g.K = K;
+        g.alpha = -1.0; g.beta_one = 1; g.lower = 1; g.row_skip = (int)skip;
+        cnt->launches += 2 + (ozaki_update_launch(g, w.oz_digits, w.oz_scale, w.oz_digits, w.oz_scale, 0, c) > 0);
+    };
     auto copy_back = [&](int64_t J, int64_t Jend, int64_t p, cudaStream_t s) {
         const int64_t rows = np - Jend * TILE;
         cudaMemcpy2DAsync(A + Jend * TILE + J * TILE * lda, lda * sizeof(double), w.pbuf[p & 1], rows * sizeof(double),
@@ -531,7 +548,7 @@ int64_t potrf_lower_head(double* A, int64_t lda, int64_t np, int64_t jb_begin, c
             const int64_t rows = np - Jend * TILE;
             if (rows == 0) break;
             solve(J, Jend, p, 0, rows, st);
-            update(J, Jend, p, 0, 0, st);
+            update_big(J, Jend, p, 0, st);
             copy_back(J, Jend, p, st.st);
             J = Jend;
             Jend = std::min(J + PT, nb);
@@ -568,7 +585,7 @@ int64_t potrf_lower_head(double* A, int64_t lda, int64_t np, int64_t jb_begin, c
         head(Jend, Jend2, p + 1);                         // ... and its head, while M applies panel p to everything else
         cudaEventRecord(la->ev_panel, la->panel);
         cudaStreamWaitEvent(st.st, w.ev_top, 0);
-        update(J, Jend, p, 0, nt2, st);
+        update_big(J, Jend, p, nt2, st);
         cudaEventRecord(la->ev_trail, st.st);
         cudaStreamWaitEvent(sc.st, w.ev_top, 0);
         if (top < rows) cudaStreamWaitEvent(sc.st, w.ev_rest, 0);

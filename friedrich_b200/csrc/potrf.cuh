@@ -116,7 +116,14 @@ struct PotrfWork {
     int* sync;        // [panels][HEAD_SYNC_INTS]
     double* pbuf[2];  // >= (np - 128) * 512 doubles each: the solved panel below its diagonal block, ld = rows below
     cudaEvent_t ev_top, ev_rest, ev_copy[2];
+    // tcgen05 trailing updates (csrc/ozaki.cuh): digit slices / row scales of the solved panel; null = f64 DMMA everywhere
+    int8_t* oz_digits = nullptr;
+    double* oz_scale = nullptr;
 };
+// the trailing update behind a panel runs on tcgen05 when at least this many rows are left below the panel (a rule on the
+// GLOBAL problem, so that the single-GPU and the sharded schedule treat every tile alike); below it the DMMA kernel's
+// smaller work items win
+constexpr int64_t OZ_MIN_ROWS = 2048;
 // `p0`: slot of the first panel's W / sync (panels are [jb_begin + 4 i, ..)); returns the number of panels factored.
 int64_t potrf_lower_head(double* A, int64_t lda, int64_t np, int64_t jb_begin, const PotrfWork& w, int64_t p0, int has_sub,
                          double sub, int* info, const LaunchCtx& st, const PotrfLookahead* la, PotrfCounters* cnt,
