@@ -14,6 +14,7 @@
 //
 // so the factorisation + broadcast of panel p+1 overlaps the trailing updates by panel p on all ranks, and when the loop
 // ends every rank holds the whole factor (replicated L: alpha solve and predict run locally, queries shard trivially).
+#include "ozaki.cuh"
 #include "sharded.cuh"
 
 #include <algorithm>
@@ -278,7 +279,20 @@ int factor_sharded_head(fgp_model* m, const fgp_kernel_desc* kd, const KernelTra
                 if (below > 0) {
                     CU(m, cudaEventRecord(m->evC, m->st2));
                     CU(m, cudaStreamWaitEvent(m->st3, m->evC, 0));
-                    gemm(A21, m->cap, prev + (Jend - Jp) * TILE, rows_p, mine, rows_p, below, wc, wp, -1.0, 1, 0, 0, sc);
+                    if (w.oz_digits && np - J * TILE >= OZ_MIN_ROWS) {
+                        // the previous panel went through the tcgen05 update (same rule, same per-tile arithmetic as the single-GPU
+                        // schedule, where these tiles belong to the main-stream launch): its digit slices start at this panel's rows
+                        CU(m, cudaStreamWaitEvent(m->st3, m->evD, 0));
+                        GemmArgs g{};
+                        g.C = A21; g.ldc = m->cap;
+                        g.M = (int)below; g.N = (int)wc; g.K = (int)wp;
+                        g.alpha = -1.0; g.beta_one = 1; g.lower = 0;
+                        const int KS = (int)(wp / OZ_KSTEP);
+                        cnt.launches += ozaki_update_launch(g, w.oz_digits + (Jend - J) * (int64_t)KS * OZ_PART_BYTES, w.oz_scale + (Jend - J) * TILE,
+                                                            w.oz_digits, w.oz_scale, 0, sc) > 0;
+                    } else {
+                        gemm(A21, m->cap, prev + (Jend - Jp) * TILE, rows_p, mine, rows_p, below, wc, wp, -1.0, 1, 0, 0, sc);
+                    }
                     CU(m, cudaEventRecord(m->evC, m->st3));
                 }
             }
@@ -314,6 +328,14 @@ int factor_sharded_head(fgp_model* m, const fgp_kernel_desc* kd, const KernelTra
         CU(m, cudaEventRecord(cm->ev_bcast, cm->st_comm));
         CU(m, cudaStreamWaitEvent(m->st2, cm->ev_bcast, 0));  // the next owner's look-ahead reads the buffer on st2 / st3
         CU(m, cudaStreamWaitEvent(m->st, cm->ev_bcast, 0));
+        // tcgen05 updates (csrc/ozaki.cuh) while >= OZ_MIN_ROWS rows are left below the panel: every rank slices the rows below the
+        // diagonal block into base-128 digits (tile 0 of the digit buffer = first row below the panel)
+        const bool oz = w.oz_digits && below >= OZ_MIN_ROWS;
+        if (oz) {
+            ozaki_slice_launch(buf + wc, rows, below, (int)wc, w.oz_digits, w.oz_scale, mc);
+            cnt.launches += 2;
+            CU(m, cudaEventRecord(m->evD, m->st));
+        }
         {
             // every owned panel c > p, c != p+1, in ONE launch: the owned panels are groups of PT tile columns, P*PT apart
             int64_t c_first = p + 1 + ((r - (p + 1)) % P + P) % P;
@@ -329,7 +351,13 @@ int factor_sharded_head(fgp_model* m, const fgp_kernel_desc* kd, const KernelTra
                 g.M = (int)(np - c0 * TILE); g.N = (int)(ncols * TILE); g.K = (int)wc;
                 g.alpha = -1.0; g.beta_one = 1; g.lower = 1;
                 g.grp = (int)PT; g.stride = (int)(P * PT);
-                cnt.launches += gemm_nt_launch(g, mc) > 0;
+                if (oz) {
+                    const int64_t toff = c0 - Jend;   // C's origin in tiles below the panel
+                    const int8_t* dg = w.oz_digits + toff * (wc / OZ_KSTEP) * (int64_t)OZ_PART_BYTES;
+                    cnt.launches += ozaki_update_launch(g, dg, w.oz_scale + toff * TILE, dg, w.oz_scale + toff * TILE, 0, mc) > 0;
+                } else {
+                    cnt.launches += gemm_nt_launch(g, mc) > 0;
+                }
             }
         }
         if (owner != r)
