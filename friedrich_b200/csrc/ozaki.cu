@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) ozaki_digits_kernel(const double* __restr
         }
         w[0][kb >> 2] |= (uint32_t)((int)X & 0xff) << (8 * (kb & 3));   // |top digit| <= 65
     }
-    int8_t* dst = digits + ((T * KS + s) * OZ_SLICES) * (int64_t)OZ_BLOCK_BYTES + kh * 2048 + (r >> 3) * 128 + (r & 7) * 16;
+    int8_t* dst = digits + ((T * KS + s) * OZ_SLICES) * (int64_t)OZ_BLOCK_BYTES + r * 32 + ((kh ^ ((r >> 2) & 1)) << 4);
 #pragma unroll
     for (int i = 0; i < OZ_SLICES; ++i)
         *reinterpret_cast<uint4*>(dst + (int64_t)i * OZ_BLOCK_BYTES) = make_uint4(w[i][0], w[i][1], w[i][2], w[i][3]);
@@ -125,12 +125,10 @@ __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_
 }
 // K-major, no swizzle: start address, leading-dimension (k direction) and stride (8-row group) byte offsets in 16 B units
 __device__ __forceinline__ uint64_t oz_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | (6ull << 61);
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr));
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, int (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
 }
 __device__ __forceinline__ void tma_wait_group_all0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
@@ -276,18 +274,22 @@ ozaki_update_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ 
                 // per element in registers.  Conversions to f64 run at 16 / clk / SM, so the integers are combined pairwise in 64-bit
                 // integer arithmetic and turned into doubles by the 2^52 trick (exact for |u| < 2^51): 3 f64 operations per element
                 double x[64];
+                int v[2][4][4];
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    int v[4][8];
+                for (int gg = 0; gg < 4; ++gg) tmem_ld4(lane_addr + gg * 128 + half * 64, v[0][gg]);
 #pragma unroll
-                    for (int gg = 0; gg < 4; ++gg) tmem_ld8(lane_addr + gg * 128 + half * 64 + ch * 8, v[gg]);
+                for (int ch = 0; ch < 16; ++ch) {   // the next 4 columns' TMEM loads are in flight while these are combined
                     tmem_ld_wait();
+                    if (ch < 15) {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const long long u = (long long)v[0][c] * 128 + v[1][c], w = (long long)v[2][c] * 128 + v[3][c];
+                        for (int gg = 0; gg < 4; ++gg) tmem_ld4(lane_addr + gg * 128 + half * 64 + (ch + 1) * 4, v[(ch + 1) & 1][gg]);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const long long u = (long long)v[ch & 1][0][c] * 128 + v[ch & 1][1][c], w = (long long)v[ch & 1][2][c] * 128 + v[ch & 1][3][c];
                         const double du = __longlong_as_double(u + 0x4338000000000000ll) - 6755399441055744.0;
                         const double dw = __longlong_as_double(w + 0x4338000000000000ll) - 6755399441055744.0;
-                        x[ch * 8 + c] = fma(du, 16384.0, dw);   // exact: < 2^47
+                        x[ch * 4 + c] = fma(du, 16384.0, dw);   // exact: < 2^47
                     }
                 }
                 tc_fence_before();

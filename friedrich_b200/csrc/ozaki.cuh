@@ -47,7 +47,7 @@ constexpr int OZ_EPI_WARPS = 8;
 constexpr int OZ_STAGING_BYTES = OZ_EPI_WARPS * 32 * 16 * 8;               // one 32 x 16 f64 image per epilogue warp
 constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + OZ_STAGING_BYTES + 1024;
 constexpr int OZ_THREADS = 32 * (2 + OZ_EPI_WARPS);
-constexpr uint32_t OZ_LBO = 2048, OZ_SBO = 128;
+constexpr uint32_t OZ_LBO = 16, OZ_SBO = 256;   // SWIZZLE_32B, K-major: 8-row groups are 256 bytes apart; LBO unused
 
 // bytes of the digit blob / doubles of the scale vector of a rows x K panel (rows % 128 == 0, K % 32 == 0)
 inline size_t ozaki_slice_bytes(int64_t rows, int K) { return (size_t)rows * (size_t)K * OZ_SLICES; }
