@@ -9,8 +9,10 @@ set of the workload.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement
  * value          fit TFLOP/s, inputs resident in HBM (fgp_refit), device time from CUDA events on the library's stream
  * e2e            same metric through the C-ABI with HOST (pinned) buffers: fgp_fit(X, y) + fgp_predict_mean_var(Xq) with
                   the H2D of X, y, Xq and the D2H of mean/var inside the timed region
- * roofline       dominant kernel = gemm_nt_kernel (SYRK/GEMM/TRSM tiles on the fp64 tensor pipe, DMMA): algorithmic
-                  flops of its launches / their summed CUDA-event durations inside the timed steps
+ * roofline       dominant kernel = ozaki_update_kernel (trailing updates on tcgen05: exact int8 digit products, int32 TMEM
+                  accumulators, 36 integer GEMMs per f64 GEMM): int8 tensor ops of its launches / their summed CUDA-event
+                  durations, against 2 x the measured bf16 tensor peak (MEASURED_PEAKS.json; the int8 rate of the tcgen05 pipe
+                  is twice the bf16 rate); `dmma` = the f64 DMMA kernel (panel solves, small updates) against the fp64 peak
  * cpu_baseline   the oracle (C restatement of the reference's algorithm, 1 thread like the reference) on a bounded sample
  * --impl reference   the reference arm: the same oracle timed on the host CPU (the Rust crate cannot be built here)
 """
@@ -41,13 +43,25 @@ WORKLOADS = {
 }
 
 
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per gemm_nt launch, averaged over the launches of one fit: read
-# from the committed ncu capture of the SHIPPED build (tools/ncu_summary.py writes the CSV; profiles/ is the judged copy).
-GEMM_TRAFFIC_CSV = {"metric": "profiles/gemm_dram_fit16k_r02.csv"}
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the dominant kernel, averaged over the launches of
+# one fit: read from the committed ncu capture of the SHIPPED build (tools/ncu_launch_csv.py writes the CSV; profiles/ is the
+# judged copy).
+GEMM_TRAFFIC_CSV = {"metric": "profiles/tcgen05_dram_fit16k_r02.csv"}
 
 
-def gemm_traffic_bytes_per_launch(workload):
-    """(bytes per launch, launches, file) from the ncu CSV rows `kernel,dram_bytes_read,dram_bytes_write` of gemm_nt_kernel, or
+def measured_peaks():
+    """MEASURED_PEAKS.json (driver-written): bf16 burst / sustained TFLOP/s and the HBM copy GB/s; fallback = the profiling
+    recipe's figures."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            mp = json.load(f)
+        return float(mp["bf16_tflops"]), float(mp.get("bf16_tflops_sustained", mp["bf16_tflops"])), "MEASURED_PEAKS.json"
+    except Exception:
+        return 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def gemm_traffic_bytes_per_launch(workload, kernel="ozaki_update_kernel"):
+    """(bytes per launch, launches, file) from the ncu CSV rows `kernel,dram_bytes_read,dram_bytes_write` of `kernel`, or
     (None, 0, file) when no capture of this build is committed."""
     rel = GEMM_TRAFFIC_CSV.get(workload)
     path = os.path.join(ROOT, rel) if rel else None
@@ -57,7 +71,7 @@ def gemm_traffic_bytes_per_launch(workload):
     total, launches = 0.0, 0
     with open(path, newline="") as f:
         for row in csv.DictReader(l for l in f if not l.startswith("#")):
-            if "gemm_nt_kernel" not in row.get("kernel", ""):
+            if kernel not in row.get("kernel", ""):
                 continue
             total += float(row["dram_bytes_read"]) + float(row["dram_bytes_write"])
             launches += 1
@@ -216,7 +230,9 @@ def workload_config(workload, world, use_sharded, lookahead=True):
     return n, d, q, {"workload": desc, "n": n, "d": d, "q": q, "noise": 0.1, "kernel": "SquaredExp(ls=sqrt(d/6), ampl=1)",
                      "l2": "inputs larger than L2 (factor = %.2f GB)" % (8.0 * n * n / 1e9),
                      "multi_gpu": ("block-cyclic 512-column panels, NCCL panel broadcast, replicated factor; queries sharded")
-                     if use_sharded else "single GPU", "lookahead": lookahead}
+                     if use_sharded else "single GPU", "lookahead": lookahead,
+                     "trailing_updates": "tcgen05.mma kind::i8 on exact base-128 digit slices (8 slices, 36 products, int32 TMEM "
+                                         "accumulators) while >= 2048 rows are left, f64 DMMA below; results are f64"}
 
 
 def weak_n(world):
@@ -290,6 +306,9 @@ def run_ours(args, rank, local_rank, world):
         return float(t.item())
 
     lib.fgp_set_profiling(h.ptr, 0)
+    if args.no_tcgen05:
+        lib.fgp_set_option(h.ptr, N.FGP_OPT_TCGEN05, 0)
+        config["trailing_updates"] = "f64 DMMA kernel everywhere (--no-tcgen05)"
     if args.no_lookahead:
         lib.fgp_set_option(h.ptr, N.FGP_OPT_LOOKAHEAD, 0)
     fit_host()  # first touch: allocations, H2D
@@ -320,8 +339,8 @@ def run_ours(args, rank, local_rank, world):
     # On one GPU the pass runs the SINGLE-STREAM schedule (look-ahead off): every launch then has the GPU to itself and its
     # event duration is the kernel's own; with look-ahead on, launches of the two streams share SMs and each one's duration
     # is inflated by the other's work (the flops and the launches are identical either way, results are bit-identical).
-    pms, pfl, pcnt = np.zeros(4), np.zeros(4), np.zeros(4, dtype=np.int64)
-    tms, tfl, tcnt = np.zeros(4), np.zeros(4), np.zeros(4, dtype=np.int64)
+    pms, pfl, pcnt = np.zeros(6), np.zeros(6), np.zeros(6, dtype=np.int64)   # classes: include/fgp.h fgp_set_profiling
+    tms, tfl, tcnt = np.zeros(6), np.zeros(6), np.zeros(6, dtype=np.int64)
     prof_dev_ms = 0.0
     if not args.no_profile:
         lib.fgp_set_profiling(h.ptr, 1)
@@ -347,6 +366,15 @@ def run_ours(args, rank, local_rank, world):
         if m_iso >= k_iso and lib.fgp_dbg_gemm_bench(local_rank, m_iso, m_iso, k_iso, 1, 1, 3, C.byref(ms_i), C.byref(fl_i)) == 0:
             iso = {"shape": f"C({m_iso}x{m_iso}, lower) -= A A^T, K={k_iso}", "ms": ms_i.value,
                    "tflops": fl_i.value / ms_i.value * 1e-9, "frac": fl_i.value / ms_i.value * 1e-9 / FP64_PEAK_TFLOPS}
+    iso_tc = None
+    if rank == 0 and not args.no_profile:
+        ms_u, ms_s = C.c_double(0), C.c_double(0)
+        m_tc = (n // 128) * 128 - 512   # the sharded schedule and the tcgen05 path always use 512-column panels
+        if m_tc >= 2048 and lib.fgp_dbg_ozaki_bench(local_rank, m_tc, 512, 3, 0, C.byref(ms_u), C.byref(ms_s)) == 0:
+            fl_tc = 2.0 * 128 * 128 * ((m_tc // 128) * (m_tc // 128 + 1) // 2) * 512
+            iso_tc = {"shape": f"C({m_tc}x{m_tc}, lower) -= P P^T, K=512, P in 8 int8 digit slices", "ms": ms_u.value,
+                      "int8_tops": 36 * fl_tc / ms_u.value * 1e-9, "f64_equivalent_tflops": fl_tc / ms_u.value * 1e-9,
+                      "digit_slicing_ms": ms_s.value}
 
     # ---- predict throughput, queries resident ------------------------------------------------------------------------
     h.check(lib.fgp_stage_queries(h.ptr, N.dptr(Xq), qr, qr))
@@ -464,9 +492,44 @@ def run_ours(args, rank, local_rank, world):
 
     value = fit_flops(n, d) / (fit_ms * 1e-3) * 1e-12
     traffic, traffic_launches, traffic_file = gemm_traffic_bytes_per_launch(args.workload) if world == 1 else (None, 0, None)
-    traffic_src = (f"{traffic_file}: dram__bytes_read.sum + dram__bytes_write.sum over the {traffic_launches} gemm_nt launches of one "
-                   f"fit of this build / launches") if traffic else "no ncu DRAM capture of this build committed for this workload"
+    traffic_src = (f"{traffic_file}: dram__bytes_read.sum + dram__bytes_write.sum over the {traffic_launches} ozaki_update_kernel "
+                   f"launches of one fit of this build / launches") if traffic else "no ncu DRAM capture of this build committed for this workload"
     gemm_tflops = tfl[0] / (tms[0] * 1e-3) * 1e-12 if tms[0] > 0 else None
+    tc_f64 = tfl[4] / (tms[4] * 1e-3) * 1e-12 if tms[4] > 0 else None   # f64-equivalent TFLOP/s of the tcgen05 launches
+    bf16_burst, bf16_sustained, peak_file = measured_peaks()
+    int8_peak = 2.0 * bf16_burst
+    dmma_block = {"kernel": "gemm_nt_kernel", "bound": "tensor", "achieved": gemm_tflops, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                  "frac": (gemm_tflops / FP64_PEAK_TFLOPS) if gemm_tflops else None, "launches": int(tcnt[0]),
+                  "share_of_step": float(tms[0] / max(prof_dev_ms, 1e-9)), "isolated": iso,
+                  "what": "f64 DMMA kernel: panel solves A21 W^T, next-diagonal-block updates, trailing updates with < 2048 rows left",
+                  "peak_source": "fp64 DMMA m8n8k4 register-resident burst measured on this pool (profiles/fp64_peak_r01.jsonl; "
+                                 "MEASURED_PEAKS.json has no fp64 figure; nominal 148 SM x 128 flop/clk x 1.965 GHz = 37.2)"}
+    if tc_f64 is not None and tms[4] >= tms[0]:
+        roofline = {"kernel": "ozaki_update_kernel", "bound": "tensor", "achieved": 36.0 * tc_f64, "peak": int8_peak,
+                    "unit": "TFLOP/s", "frac": 36.0 * tc_f64 / int8_peak,
+                    "op": "int8 tensor operations (2 per multiply-add) of tcgen05.mma kind::i8: 36 digit-slice products of "
+                          "2*128*128*K per 128x128 tile (SURVEY 8(d)'s 2 m n k per f64 GEMM x 36)",
+                    "f64_equivalent_tflops": tc_f64, "f64_equivalent_over_dmma_peak": tc_f64 / FP64_PEAK_TFLOPS,
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "launches": int(tcnt[4]), "share_of_step": float(tms[4] / max(prof_dev_ms, 1e-9)),
+                    "frac_of_sustained_peak": 36.0 * tc_f64 / (2.0 * bf16_sustained),
+                    "note": "rank 0; achieved = int8 tensor ops of ALL tcgen05 trailing-update launches of a fit / sum of their "
+                            "CUDA-event durations, from a separate pass of the same steps with per-launch events on and, on one "
+                            "GPU, the single-stream schedule so launches do not share SMs; `isolated` = the dominant launch "
+                            "shape alone, measured live; the kernel runs into the 1 kW power cap (tools/ozaki_clocks.py: SM "
+                            "clock 1965 -> ~1650 MHz when it runs back to back), which is what the sustained figure reflects",
+                    "isolated": iso_tc, "profiled_ms_per_step": prof_dev_ms / args.steps,
+                    "peak_source": f"2 x bf16_tflops of {peak_file} (burst {bf16_burst:.1f}, sustained {bf16_sustained:.1f} TFLOP/s; "
+                                   f"the int8 rate of the tcgen05 pipe is twice its bf16 rate; nominal 4500)",
+                    "dmma": dmma_block}
+    else:
+        roofline = dict(dmma_block)
+        roofline.update({"traffic": None, "traffic_source": "no capture for this configuration",
+                         "profiled_ms_per_step": prof_dev_ms / args.steps,
+                         "note": "rank 0; the tcgen05 path is off or minor in this configuration: f64 DMMA kernel, achieved = "
+                                 "algorithmic flops of all its launches / sum of their CUDA-event durations (profiling pass)",
+                         "tcgen05": {"f64_equivalent_tflops": tc_f64, "launches": int(tcnt[4]),
+                                     "share_of_step": float(tms[4] / max(prof_dev_ms, 1e-9)), "isolated": iso_tc}})
     line = {
         "metric": "gp_fit_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": fit_ms, "higher_is_better": True,
@@ -485,24 +548,13 @@ def run_ours(args, rank, local_rank, world):
                 "what": ("fgp_fit_sharded(rank-0 host X, y) + " if use_sharded else "fgp_fit(host X, y) + ") +
                         "fgp_predict_mean_var(host Xq) -> host mean, var"},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "gemm_nt_kernel", "bound": "tensor", "achieved": gemm_tflops, "peak": FP64_PEAK_TFLOPS,
-                     "unit": "TFLOP/s", "frac": (gemm_tflops / FP64_PEAK_TFLOPS) if gemm_tflops else None,
-                     "traffic": traffic, "traffic_source": traffic_src,
-                     "launches": int(tcnt[0]), "share_of_step": float(tms[0] / max(prof_dev_ms, 1e-9)),
-                     "note": "rank 0; achieved = algorithmic flops of ALL gemm_nt launches of a fit (from the 56-wave trailing "
-                             "updates down to sub-wave panel products) / sum of their CUDA-event durations, from a separate "
-                             "pass of the same steps with per-launch events on and, on one GPU, the single-stream schedule "
-                             "so launches do not share SMs; `isolated` = the dominant launch shape alone, measured live",
-                     "isolated": iso,
-                     "profiled_ms_per_step": prof_dev_ms / args.steps,
-                     "peak_source": "fp64 DMMA m8n8k4 register-resident burst measured on this pool "
-                                    "(profiles/fp64_peak_r01.jsonl; MEASURED_PEAKS.json has no fp64 figure; nominal "
-                                    "148 SM x 128 flop/clk x 1.965 GHz = 37.2; sustained DMMA loop 27.4)"},
-        "kernel_ms_per_step": {"gemm_nt": tms[0] / args.steps, "potrf_head": tms[1] / args.steps,
-                               "gram": tms[2] / args.steps},
+        "roofline": roofline,
+        "kernel_ms_per_step": {"tcgen05_update": tms[4] / args.steps, "digit_slicing": tms[5] / args.steps,
+                               "gemm_nt": tms[0] / args.steps, "potrf_head": tms[1] / args.steps, "gram": tms[2] / args.steps},
         # what bounds a step: summed kernel time per class from the profiling pass (on one GPU: single-stream schedule, so
         # the sum IS the step) next to the overlapped step; the head kernels are the serial chain, the rest is GEMM
         "step_breakdown_ms": {"overlapped_step": fit_ms, "serialised_step": prof_dev_ms / max(args.steps, 1),
+                              "tcgen05_updates": tms[4] / args.steps, "digit_slicing": tms[5] / args.steps,
                               "gemm": tms[0] / args.steps, "panel_heads": tms[1] / args.steps, "gram": tms[2] / args.steps,
                               "bcast_as_owner": (tms[3] / args.steps) if use_sharded else 0.0,
                               "panel_head_launches": int(tcnt[1] // max(args.steps, 1))},
@@ -545,6 +597,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lookahead", action="store_true", help="A/B: single-stream Cholesky schedule")
     ap.add_argument("--no-profile", action="store_true", help="A/B: no per-launch CUDA events (roofline fields become null)")
+    ap.add_argument("--no-tcgen05", action="store_true", help="A/B: f64 DMMA kernel for every trailing update (round-1 arithmetic)")
     ap.add_argument("--sharded", action="store_true", help="use the collective entry points even on one GPU")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling C4 block")
     args = ap.parse_args()

@@ -28,16 +28,16 @@ inline bool* per_device_flag(bool (&flags)[64]) {
 // ---------------------------------------------------------------------------------------------------------------
 // Launch context: the stream plus an optional per-kernel-class profiler (CUDA events around each launch on the
 // launching stream; bench.py's roofline figures come from it, include/fgp.h fgp_set_profiling).
-enum ProfClass { PROF_GEMM = 0, PROF_POTRF_DIAG = 1, PROF_PAIR = 2, PROF_OTHER = 3, PROF_NCLASS = 4 };
+enum ProfClass { PROF_GEMM = 0, PROF_POTRF_DIAG = 1, PROF_PAIR = 2, PROF_OTHER = 3, PROF_TCGEN05 = 4, PROF_SLICE = 5, PROF_NCLASS = 6 };
 
 struct Profiler {
     struct Rec { int cls; double flops; cudaEvent_t e0, e1; };
     std::vector<cudaEvent_t> pool;
     size_t used = 0;
     std::vector<Rec> recs;
-    double ms[PROF_NCLASS] = {0, 0, 0, 0};
-    double flops[PROF_NCLASS] = {0, 0, 0, 0};
-    int64_t count[PROF_NCLASS] = {0, 0, 0, 0};
+    double ms[PROF_NCLASS] = {};
+    double flops[PROF_NCLASS] = {};
+    int64_t count[PROF_NCLASS] = {};
     cudaEvent_t get() {
         if (used == pool.size()) {
             cudaEvent_t e;

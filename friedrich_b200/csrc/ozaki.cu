@@ -351,7 +351,7 @@ cudaError_t ozaki_prepare() {
 
 void ozaki_slice_launch(const double* P, int64_t ld, int64_t rows, int K, int8_t* digits, double* scale, const LaunchCtx& ctx) {
     if (rows <= 0 || K <= 0) return;
-    ProfScope ps(ctx, PROF_OTHER, 0.0);
+    ProfScope ps(ctx, PROF_SLICE, 16.0 * (double)rows * K);   // "flops" slot: bytes moved (8 read + 8 written per element)
     ozaki_rowmax_kernel<<<(unsigned)(rows / 128), 1024, 0, ctx.st>>>(P, ld, K, scale);
     ozaki_digits_kernel<<<dim3((unsigned)(rows / 128), (unsigned)(K / OZ_KSTEP)), 256, 0, ctx.st>>>(P, ld, K / OZ_KSTEP, scale, digits);
 }
@@ -387,7 +387,7 @@ int64_t ozaki_update_launch(const GemmArgs& g, const int8_t* digitsA, const doub
     o.lbo = lbo; o.sbo = sbo;
     o.exp = g_oz_exp;
     const unsigned grid = (unsigned)((tiles + tpc - 1) / tpc);
-    ProfScope ps(ctx, PROF_GEMM, gemm_nt_flops(g));
+    ProfScope ps(ctx, PROF_TCGEN05, gemm_nt_flops(g));   // f64-equivalent flops; the int8 tensor work is 36 x that
     ozaki_update_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, ctx.st>>>(p, tmC, o);
     return tiles;
 }

@@ -165,8 +165,9 @@ double fgp_comm_last_bytes(const fgp_model* m);
 double fgp_last_device_ms(const fgp_model* m);
 int64_t fgp_last_launch_count(const fgp_model* m);
 /* Per-kernel-class device timing of the last entry-point call (CUDA events around every launch on the model's stream).
- * Classes: 0 = gemm_nt (SYRK / GEMM / TRSM-as-GEMM, fp64 tensor pipe), 1 = potrf_diag, 2 = pair tiles (Gram,
- * cross-covariance, gradient reductions), 3 = other.  ms / flops / count are arrays of 4. */
+ * Classes: 0 = gemm_nt (SYRK / GEMM / TRSM-as-GEMM, fp64 tensor pipe), 1 = potrf_diag / panel heads, 2 = pair tiles (Gram,
+ * cross-covariance, gradient reductions), 3 = other, 4 = tcgen05 trailing updates (flops = f64-equivalent; the int8 tensor
+ * work is 36 x that), 5 = digit slicing for them (flops slot = bytes moved).  ms / flops / count are arrays of 6. */
 int fgp_set_profiling(fgp_model* m, int on);
 /* Scheduling knobs (results are identical either way; used by bench.py / tests for A-B runs).
  * FGP_OPT_LOOKAHEAD (default 1): factor the next panel on a second, high-priority stream while the trailing update
