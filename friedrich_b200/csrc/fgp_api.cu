@@ -80,6 +80,7 @@ void solve_alpha(fgp_model* m) {
 int rebuild_panel_inverses(fgp_model* m) {
     m->pstart.clear();
     m->w_valid = false;
+    m->ozL_valid = false;
     return FGP_OK;
 }
 
@@ -112,6 +113,32 @@ int prepare_head_work(fgp_model* m, int64_t jb_begin, PotrfWork* w, int64_t* p0)
         if (ozaki_prepare() != cudaSuccess) return fail(m, FGP_ERR_CUDA, "tcgen05 update kernel could not be configured");
         w->oz_digits = reinterpret_cast<int8_t*>(m->ozDigits.p);
         w->oz_scale = m->ozScale.p;
+        m->ozL_valid = false;
+        if (jb_begin == 0 && !m->comm) {
+            // full single-GPU fit: every panel with >= OZ_MIN_ROWS rows below it keeps its digit slices (8 bytes per element of
+            // L below the panel's diagonal block: as many bytes as that part of L) for the solves of predict
+            m->ozOffBytes.assign((size_t)slots, -1);
+            m->ozOffRows.assign((size_t)slots, -1);
+            int64_t bytes = 0, rows_total = 0;
+            for (int64_t s = 0; s < slots; ++s) {
+                const int64_t J = m->pstart[s], Jend = std::min<int64_t>(J + PT, nb), rows = m->np - Jend * TILE;
+                if (rows < OZ_MIN_ROWS) continue;
+                m->ozOffBytes[s] = bytes;
+                m->ozOffRows[s] = rows_total;
+                bytes += (int64_t)ozaki_slice_bytes(rows, (int)((Jend - J) * TILE));
+                rows_total += rows;
+            }
+            if (bytes > 0) {
+                CU(m, m->ozL.reserve((size_t)bytes / 8));
+                CU(m, m->ozLscale.reserve((size_t)rows_total));
+                w->oz_digits = reinterpret_cast<int8_t*>(m->ozL.p);
+                w->oz_scale = m->ozLscale.p;
+                w->oz_off_bytes = m->ozOffBytes.data();
+                w->oz_off_rows = m->ozOffRows.data();
+            }
+        }
+    } else {
+        m->ozL_valid = false;
     }
     return FGP_OK;
 }
@@ -161,6 +188,7 @@ int factor_resident(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits&
         potrf_lower_head(m->L.p, m->cap, m->np, 0, w, p0, has_eps, eps, m->info_d, m->ctx(), m->lookahead ? &la : nullptr, &cnt,
                          &rest);
         m->w_valid = true;
+        m->ozL_valid = w.oz_off_bytes != nullptr;
     } else {
         potrf_lower(m->L.p, m->cap, m->np, 0, m->inv.p, m->invT.p, has_eps, eps, m->info_d, m->ctx(),
                     m->lookahead ? &la : nullptr, &cnt, &rest);
@@ -302,9 +330,17 @@ int predict_device(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& 
     }
     if (want_var) {
         if (m->w_valid && !m->pstart.empty() && qp <= m->cap)  // panels of the head schedule: two K <= 512 launches per 512 columns
+        {
+            // updates behind a panel whose digit slices the fit kept run on tcgen05 (the solved panel of Bt is sliced on the fly)
+            OzPanelStore ozs{};
+            const bool use_oz = m->tcgen05 && m->ozL_valid && m->ozOffBytes.size() == m->pstart.size() && qp <= m->cap && m->ozDigits.p;
+            if (use_oz)
+                ozs = OzPanelStore{reinterpret_cast<const int8_t*>(m->ozL.p), m->ozLscale.p, m->ozOffBytes.data(), m->ozOffRows.data(),
+                                   reinterpret_cast<int8_t*>(m->ozDigits.p), m->ozScale.p};
             m->launches += trsm_fwd_t_panels(m->bt.p, qp, qp, m->L.p, m->cap, m->Wp.p, m->pstart.data(), (int64_t)m->pstart.size(),
                                              np / TILE, np / TILE, m->pbuf[0].p, m->pbuf[1].p, m->ctx(),
-                                             m->lookahead ? m->st2 : nullptr, m->evA, m->evB, m->evC);
+                                             m->lookahead ? m->st2 : nullptr, m->evA, m->evB, m->evC, use_oz ? &ozs : nullptr);
+        }
         else if (m->lookahead)
             m->launches += trsm_fwd_t_lookahead(m->bt.p, qp, qp, m->L.p, m->cap, m->inv.p, np / TILE, m->ctx(), m->st2, m->evA,
                                                 m->evB);
@@ -939,6 +975,7 @@ FGP_EXPORT int fgp_add_samples(fgp_model* m, const double* Xnew, int64_t ldx, in
     const int64_t Mrows = np_new - jb * TILE;
     if (m->head_schedule) {
         const bool had_w = m->w_valid;
+        m->ozL_valid = false;   // the kept digit slices do not cover the new rows
         PotrfWork w;
         int64_t p0 = 0;
         FGP_TRY(prepare_head_work(m, jb, &w, &p0));  // panel table: the old panels (the last one cut at jb), then the new ones

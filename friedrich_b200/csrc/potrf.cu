@@ -527,12 +527,18 @@ int64_t potrf_lower_head(double* A, int64_t lda, int64_t np, int64_t jb_begin, c
             return;
         }
         const int K = (int)((Jend - J) * TILE);
-        ozaki_slice_launch(w.pbuf[p & 1], rows, rows, K, w.oz_digits, w.oz_scale, c);
+        int8_t* dg = w.oz_digits;
+        double* sc = w.oz_scale;
+        if (w.oz_off_bytes && w.oz_off_bytes[p0 + p] >= 0) {   // kept for the solves of predict (trsm.cuh)
+            dg += w.oz_off_bytes[p0 + p];
+            sc += w.oz_off_rows[p0 + p];
+        }
+        ozaki_slice_launch(w.pbuf[p & 1], rows, rows, K, dg, sc, c);
         GemmArgs g{};
         g.C = A + Jend * TILE * (lda + 1); g.ldc = lda;
         g.M = (int)rows; g.N = g.M; g.K = K;
         g.alpha = -1.0; g.beta_one = 1; g.lower = 1; g.row_skip = (int)skip;
-        cnt->launches += 2 + (ozaki_update_launch(g, w.oz_digits, w.oz_scale, w.oz_digits, w.oz_scale, 0, c) > 0);
+        cnt->launches += 2 + (ozaki_update_launch(g, dg, sc, dg, sc, 0, c) > 0);
     };
     auto copy_back = [&](int64_t J, int64_t Jend, int64_t p, cudaStream_t s) {
         const int64_t rows = np - Jend * TILE;

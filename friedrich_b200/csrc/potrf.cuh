@@ -119,6 +119,10 @@ struct PotrfWork {
     // tcgen05 trailing updates (csrc/ozaki.cuh): digit slices / row scales of the solved panel; null = f64 DMMA everywhere
     int8_t* oz_digits = nullptr;
     double* oz_scale = nullptr;
+    // optional (full single-GPU fits): panel slot s keeps its digits at oz_digits + oz_off_bytes[s] / oz_scale + oz_off_rows[s]
+    // (-1: the panel has fewer than OZ_MIN_ROWS rows below it and is never sliced); null: one scratch image, reused per panel
+    const int64_t* oz_off_bytes = nullptr;
+    const int64_t* oz_off_rows = nullptr;
 };
 // the trailing update behind a panel runs on tcgen05 when at least this many rows are left below the panel (a rule on the
 // GLOBAL problem, so that the single-GPU and the sharded schedule treat every tile alike); below it the DMMA kernel's

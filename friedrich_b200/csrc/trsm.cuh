@@ -15,6 +15,7 @@
 #pragma once
 
 #include "gemm_nt.cuh"
+#include "ozaki.cuh"
 
 namespace fgp {
 
@@ -126,10 +127,22 @@ inline int64_t trsm_fwd_t_lookahead(double* Xt, int64_t ldx, int64_t M, const do
 // Xt ARE the new block rows of L, so L[later, panel] for those columns is the panel just solved (copied back before the
 // update reads it) and the new diagonal block receives  -= T T^T  panel by panel, in order (no K = n SYRK at the end).
 // Returns the number of launches; ends joined on st.st.
+// `ozs` (optional; predict only: upd_end == i_end): digit slices of L[below, panel] kept by the fit (model.cuh ozL).  The main
+// update of a panel that has them runs on tcgen05 (csrc/ozaki.cuh): T is sliced into the scratch image, then
+// Xt[:, later] -= T L[later, panel]^T as exact int8 products; panels without digits (fewer than OZ_MIN_ROWS rows below) and
+// the next panel's columns on the panel stream keep the f64 DMMA kernel.
+struct OzPanelStore {
+    const int8_t* digits;
+    const double* scale;
+    const int64_t* off_bytes;   // per panel, -1 = none
+    const int64_t* off_rows;
+    int8_t* scratch;            // >= M x 512 x 8 bytes
+    double* scratch_scale;      // >= M doubles
+};
 inline int64_t trsm_fwd_t_panels(double* Xt, int64_t ldx, int64_t M, const double* L, int64_t ldl, const double* W,
                                  const int64_t* pstart, int64_t npanels, int64_t i_end, int64_t upd_end, double* tmp0,
                                  double* tmp1, const LaunchCtx& st, cudaStream_t panel_stream, cudaEvent_t ev_panel,
-                                 cudaEvent_t ev_trail0, cudaEvent_t ev_trail1) {
+                                 cudaEvent_t ev_trail0, cudaEvent_t ev_trail1, const OzPanelStore* ozs = nullptr) {
     constexpr int64_t WP = 512;
     int64_t launches = 0;
     LaunchCtx pc = st;
@@ -148,6 +161,23 @@ inline int64_t trsm_fwd_t_panels(double* Xt, int64_t ldx, int64_t M, const doubl
     };
     auto pend = [&](int64_t p) { return p + 1 < npanels ? pstart[p + 1] : i_end; };
     if (upd_end < i_end) upd_end = i_end;
+    // Xt[:, block columns [c0, upd_end)] -= T L[those rows, panel p]^T on the main stream: tcgen05 when the panel's digits exist
+    auto update_main = [&](int64_t p, int64_t J, int64_t Jend, int64_t c0, int64_t w, const double* tmp) {
+        if (c0 >= upd_end) return;
+        if (ozs && upd_end == i_end && ozs->off_bytes[p] >= 0) {
+            ozaki_slice_launch(tmp, M, M, (int)w, ozs->scratch, ozs->scratch_scale, st);
+            GemmArgs g{};
+            g.C = Xt + c0 * TILE * ldx; g.ldc = ldx;
+            g.M = (int)M; g.N = (int)((upd_end - c0) * TILE); g.K = (int)w;
+            g.alpha = -1.0; g.beta_one = 1; g.lower = 0;
+            const int64_t toff = c0 - Jend;   // the panel's digit image starts at the first row below its diagonal block
+            launches += 2 + (ozaki_update_launch(g, ozs->scratch, ozs->scratch_scale,
+                                                 ozs->digits + ozs->off_bytes[p] + toff * (w / OZ_KSTEP) * (int64_t)OZ_PART_BYTES,
+                                                 ozs->scale + ozs->off_rows[p] + toff * TILE, 0, st) > 0);
+        } else {
+            gemm(Xt + c0 * TILE * ldx, ldx, tmp, M, L + c0 * TILE + J * TILE * ldl, ldl, (upd_end - c0) * TILE, w, -1.0, 1, 0, st);
+        }
+    };
     if (two) {
         cudaEventRecord(ev_trail0, st.st);  // the panel stream starts after whatever filled Xt on the main stream
         cudaStreamWaitEvent(panel_stream, ev_trail0, 0);
@@ -170,11 +200,10 @@ inline int64_t trsm_fwd_t_panels(double* Xt, int64_t ldx, int64_t M, const doubl
             cudaEventRecord(ev_panel, panel_stream);
             gemm(Xt + Jend * TILE * ldx, ldx, tmp, M, L + Jend * TILE + J * TILE * ldl, ldl, (Jnext - Jend) * TILE, w, -1.0, 1, 0, pc);
             cudaStreamWaitEvent(st.st, ev_panel, 0);
-            gemm(Xt + Jnext * TILE * ldx, ldx, tmp, M, L + Jnext * TILE + J * TILE * ldl, ldl, (upd_end - Jnext) * TILE, w, -1.0, 1, 0,
-                 st);
+            update_main(p, J, Jend, Jnext, w, tmp);
             cudaEventRecord(ev_trail, st.st);
         } else {
-            gemm(Xt + Jend * TILE * ldx, ldx, tmp, M, L + Jend * TILE + J * TILE * ldl, ldl, (upd_end - Jend) * TILE, w, -1.0, 1, 0, st);
+            update_main(p, J, Jend, Jend, w, tmp);
         }
     }
     if (two) {
