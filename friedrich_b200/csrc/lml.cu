@@ -1,5 +1,8 @@
 // lml.cu — LML-gradient reductions and the bandwidth heuristic on the pair-tile engine (contract in lml.cuh).
 #include "lml.cuh"
+#include "ozaki.cuh"
+#include "potrf.cuh"
+#include "trsm.cuh"
 
 #include "potrf.cuh"
 #include "sharded.cuh"
@@ -117,7 +120,22 @@ int lml_gradient_device(fgp_model* m, const fgp_kernel_desc* kd, const KernelTra
     CU(m, cudaMemsetAsync(m->U.p, 0, (size_t)np * np * sizeof(double), m->st));
     set_identity_kernel<<<(unsigned)((np + 255) / 256), 256, 0, m->st>>>(m->U.p, np, np);
     m->launches += 1;
-    m->launches += trsm_fwd_t(m->U.p, np, np, m->L.p, m->cap, m->inv.p, 0, nb, nullptr, m->ctx(), true);
+    const bool panels = m->w_valid && !m->pstart.empty() && np <= m->cap && m->pbuf[0].p && m->pbuf[1].p;
+    const bool tc = m->tcgen05 && np >= OZ_MIN_ROWS && np <= 32768 && ozaki_prepare() == cudaSuccess;
+    if (panels) {
+        // over the panels of the head schedule (W_p = L11^-1 per panel): two launches per 512 columns; where the fit kept the
+        // panel's digit slices the K = 512 updates run on tcgen05 (trsm.cuh)
+        OzPanelStore ozs{};
+        const bool use_oz = tc && m->ozL_valid && m->ozOffBytes.size() == m->pstart.size() && m->ozDigits.p;
+        if (use_oz)
+            ozs = OzPanelStore{reinterpret_cast<const int8_t*>(m->ozL.p), m->ozLscale.p, m->ozOffBytes.data(), m->ozOffRows.data(),
+                               reinterpret_cast<int8_t*>(m->ozDigits.p), m->ozScale.p};
+        m->launches += trsm_fwd_t_panels(m->U.p, np, np, m->L.p, m->cap, m->Wp.p, m->pstart.data(), (int64_t)m->pstart.size(), nb, nb,
+                                         m->pbuf[0].p, m->pbuf[1].p, m->ctx(), m->lookahead ? m->st2 : nullptr, m->evA, m->evB, m->evC,
+                                         use_oz ? &ozs : nullptr, true);
+    } else {
+        m->launches += trsm_fwd_t(m->U.p, np, np, m->L.p, m->cap, m->inv.p, 0, nb, nullptr, m->ctx(), true);
+    }
     // K^-1 = U U^T, lower triangle
     {
         GemmArgs g{};
@@ -126,7 +144,22 @@ int lml_gradient_device(fgp_model* m, const fgp_kernel_desc* kd, const KernelTra
         g.B = m->U.p; g.ldb = np;
         g.M = g.N = (int)np; g.K = (int)np;
         g.alpha = 1.0; g.beta_one = 0; g.lower = 1; g.k_from_tile = 1;
-        m->launches += gemm_nt_launch(g, m->ctx()) > 0;
+        bool done = false;
+        if (tc) {
+            // on tcgen05: the rows of U in 8 digit slices (np x np x 8 bytes), exact int8 products accumulated in int32 over the whole
+            // contraction (8 np 65 64 < 2^31 up to np = 32768), added to a zeroed K^-1
+            if (m->ozU.reserve((size_t)np * np) == cudaSuccess && m->ozScale.reserve((size_t)std::max<int64_t>(np, m->cap)) == cudaSuccess) {
+                int8_t* dg = reinterpret_cast<int8_t*>(m->ozU.p);
+                ozaki_slice_launch(m->U.p, np, np, (int)np, dg, m->ozScale.p, m->ctx());
+                CU(m, cudaMemsetAsync(m->Kinv.p, 0, (size_t)np * np * sizeof(double), m->st));
+                g.beta_one = 1;
+                m->launches += 2 + (ozaki_update_launch(g, dg, m->ozScale.p, dg, m->ozScale.p, 0, m->ctx()) > 0);
+                done = true;
+            } else {
+                cudaGetLastError();
+            }
+        }
+        if (!done) m->launches += gemm_nt_launch(g, m->ctx()) > 0;
     }
     // fused gradient reductions
     PairArgs pa{};

@@ -75,6 +75,7 @@ struct fgp_model {
     fgp::DevBuf ozL, ozLscale;             // digit slices / row scales of EVERY panel of L with >= OZ_MIN_ROWS rows below it, kept by a
     std::vector<int64_t> ozOffBytes, ozOffRows;   // full single-GPU fit for the solves of predict: per panel byte / row offset, -1 = none
     bool ozL_valid = false;
+    fgp::DevBuf ozU;                       // digit slices of U = L^-T for K^-1 = U U^T on tcgen05 (LML gradient)
     int* head_sync = nullptr;              // [head_sync_cap][HEAD_SYNC_INTS]
     int64_t head_sync_cap = 0;
     std::vector<int64_t> pstart;           // first block column of every panel of the current factor (W slot = index)

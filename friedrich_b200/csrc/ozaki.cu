@@ -83,6 +83,7 @@ struct OzArgs {
     int KS;          // k-steps (K / 32)
     int tiles, tpc;  // tiles of the launch, tiles per CTA (CTA b: tiles [b * tpc, (b + 1) * tpc))
     uint32_t lbo, sbo;
+    double alpha;    // C += alpha * P Q^T (the factorisation uses -1; K^-1 = U U^T uses +1 on a zeroed C)
     int exp;         // measurement switches (tools/ozaki_check.py): 1 = no epilogue arithmetic / stores, 2 = no operand copies, 4 = no MMAs
 };
 
@@ -206,9 +207,11 @@ ozaki_update_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ 
             gemm_tile_decode(g, t, ti, tj);
             const int8_t* a0 = o.SA + (int64_t)ti * o.KS * OZ_PART_BYTES;
             const int8_t* b0 = o.SB + (int64_t)tj * o.KS * OZ_PART_BYTES;
+            // k_from_tile (U U^T on upper-triangular operands): the contraction starts at k = 128 (k_tile0 + max(ti, tj))
+            const int ks0 = g.k_from_tile ? (128 / OZ_KSTEP) * (g.k_tile0 + max(ti, tj)) : 0;
             for (int pass = 0; pass < 2; ++pass) {
                 const uint32_t bytes = pass == 0 ? OZ_PART_BYTES / 2 : OZ_PART_BYTES;
-                for (int ks = 0; ks < o.KS; ++ks) {
+                for (int ks = ks0; ks < o.KS; ++ks) {
                     oz_wait(&empty[stage], phase ^ 1);
                     if (elect_one()) {
                         unsigned char* dst = ring + stage * OZ_STAGE_BYTES;
@@ -233,17 +236,23 @@ ozaki_update_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ 
         const uint32_t hi = (uint32_t)(oz_desc(0, o.lbo, o.sbo) >> 32), lbo_field = (o.lbo >> 4) << 16;
         const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFFu) >> 4) | lbo_field;
         for (int t = t_begin; t < t_end; ++t) {
+            int ks0 = 0;
+            if (g.k_from_tile) {
+                int ti, tj;
+                gemm_tile_decode(g, t, ti, tj);
+                ks0 = (128 / OZ_KSTEP) * (g.k_tile0 + max(ti, tj));
+            }
             for (int pass = 0; pass < 2; ++pass, ++npass) {
                 oz_wait(tmem_empty, (npass & 1) ^ 1);   // the epilogue has drained the four accumulators
                 tc_fence_after();
-                for (int ks = 0; ks < o.KS; ++ks) {
+                for (int ks = ks0; ks < o.KS; ++ks) {
                     oz_wait(&full[stage], phase);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t a_lo = ring_lo + stage * (OZ_STAGE_BYTES >> 4), b_lo = a_lo + (OZ_PART_BYTES >> 4);
                         if (!(o.exp & 4)) {
-                            if (pass == 0) issue_kstep<0>(tmem_base, a_lo, b_lo, hi, ks > 0);
-                            else issue_kstep<1>(tmem_base, a_lo, b_lo, hi, ks > 0);
+                            if (pass == 0) issue_kstep<0>(tmem_base, a_lo, b_lo, hi, ks > ks0);
+                            else issue_kstep<1>(tmem_base, a_lo, b_lo, hi, ks > ks0);
                         }
                         tc_commit(&empty[stage]);                    // the stage is free once these MMAs have read it
                         if (ks == o.KS - 1) tc_commit(tmem_full);    // accumulators complete
@@ -266,8 +275,8 @@ ozaki_update_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ 
             const int m0 = ti * 128, n0 = tj * 128;
             const double rs = o.scA[m0 + row];
             for (int pass = 0; pass < 2; ++pass, ++npass) {
-                // pass 0 carries the groups 0..3: weight 128^4 = 2^28 over pass 1; alpha = -1; sc = 2^(e-30): 2^(e_r+e_c-61) = rs*cs/2
-                const double rf = rs * (pass == 0 ? -134217728.0 : -0.5);
+                // pass 0 carries the groups 0..3: weight 128^4 = 2^28 over pass 1; sc = 2^(e-30): 2^(e_r+e_c-61) = rs*cs/2
+                const double rf = rs * o.alpha * (pass == 0 ? 134217728.0 : 0.5);
                 oz_wait(tmem_full, npass & 1);
                 tc_fence_after();
                 // phase 1 (TMEM busy, the MMA warp waits): the warp's 32 rows x 64 columns of the four accumulators -> one exact f64
@@ -386,6 +395,7 @@ int64_t ozaki_update_launch(const GemmArgs& g, const int8_t* digitsA, const doub
     o.tpc = tpc;
     o.lbo = lbo; o.sbo = sbo;
     o.exp = g_oz_exp;
+    o.alpha = g.alpha;
     const unsigned grid = (unsigned)((tiles + tpc - 1) / tpc);
     ProfScope ps(ctx, PROF_TCGEN05, gemm_nt_flops(g));   // f64-equivalent flops; the int8 tensor work is 36 x that
     ozaki_update_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, ctx.st>>>(p, tmC, o);

@@ -56,8 +56,9 @@ cudaError_t ozaki_prepare();
 void ozaki_set_experiment(int flags);  // measurement switches of the update kernel (0 = production)
 // digits + row scales (2^(e_r - 30), 0 for an all-zero row, NaN when the row holds a non-finite value) of P (column-major, ld)
 void ozaki_slice_launch(const double* P, int64_t ld, int64_t rows, int K, int8_t* digits, double* scale, const LaunchCtx& ctx);
-// C -= P P^T on the tiles GemmArgs describes (C, ldc, M, N, lower, row_skip, grp, stride, K; alpha = -1, beta = 1 implied);
-// tile row ti reads row tile ti of (digitsA, scaleA), tile column tj row tile tj of (digitsB, scaleB).
+// C += alpha * P Q^T on the tiles GemmArgs describes (C, ldc, M, N, K, alpha = +-1, lower, row_skip, grp, stride, k_from_tile,
+// k_tile0; beta = 1 implied: a plain product needs C zeroed first); tile row ti reads row tile ti of (digitsA, scaleA), tile
+// column tj row tile tj of (digitsB, scaleB).  K <= 32768 keeps the int32 accumulators exact (8 K 65 64 < 2^31).
 // tiles_per_cta <= 0: default. Returns the number of tiles launched.
 int64_t ozaki_update_launch(const GemmArgs& g, const int8_t* digitsA, const double* scaleA, const int8_t* digitsB,
                             const double* scaleB, int tiles_per_cta, const LaunchCtx& ctx, uint32_t lbo = OZ_LBO,

@@ -142,12 +142,16 @@ struct OzPanelStore {
 inline int64_t trsm_fwd_t_panels(double* Xt, int64_t ldx, int64_t M, const double* L, int64_t ldl, const double* W,
                                  const int64_t* pstart, int64_t npanels, int64_t i_end, int64_t upd_end, double* tmp0,
                                  double* tmp1, const LaunchCtx& st, cudaStream_t panel_stream, cudaEvent_t ev_panel,
-                                 cudaEvent_t ev_trail0, cudaEvent_t ev_trail1, const OzPanelStore* ozs = nullptr) {
+                                 cudaEvent_t ev_trail0, cudaEvent_t ev_trail1, const OzPanelStore* ozs = nullptr,
+                                 bool tri_rows = false) {
+    // `tri_rows`: the right-hand side is the identity (U = L^-T): the columns of panel [J, Jend) are non-zero in the first
+    // 128 Jend rows only, so every product of the panel works on Mi = min(M, 128 Jend) rows (n^3/3 instead of n^3 flops)
     constexpr int64_t WP = 512;
     int64_t launches = 0;
     LaunchCtx pc = st;
     const bool two = panel_stream != nullptr;
     if (two) pc.st = panel_stream;
+    int64_t Mi = M;   // rows the current panel's products work on
     auto gemm = [&](double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t N, int64_t K,
                     double alpha, int beta_one, int k_upto, const LaunchCtx& c) {
         if (N <= 0) return;
@@ -155,7 +159,7 @@ inline int64_t trsm_fwd_t_panels(double* Xt, int64_t ldx, int64_t M, const doubl
         g.C = C; g.ldc = ldc;
         g.A = A; g.lda = lda;
         g.B = B; g.ldb = ldb;
-        g.M = (int)M; g.N = (int)N; g.K = (int)K;
+        g.M = (int)Mi; g.N = (int)N; g.K = (int)K;
         g.alpha = alpha; g.beta_one = beta_one; g.lower = 0; g.k_upto_col = k_upto;
         launches += gemm_nt_launch(g, c) > 0;
     };
@@ -165,10 +169,10 @@ inline int64_t trsm_fwd_t_panels(double* Xt, int64_t ldx, int64_t M, const doubl
     auto update_main = [&](int64_t p, int64_t J, int64_t Jend, int64_t c0, int64_t w, const double* tmp) {
         if (c0 >= upd_end) return;
         if (ozs && upd_end == i_end && ozs->off_bytes[p] >= 0) {
-            ozaki_slice_launch(tmp, M, M, (int)w, ozs->scratch, ozs->scratch_scale, st);
+            ozaki_slice_launch(tmp, M, Mi, (int)w, ozs->scratch, ozs->scratch_scale, st);
             GemmArgs g{};
             g.C = Xt + c0 * TILE * ldx; g.ldc = ldx;
-            g.M = (int)M; g.N = (int)((upd_end - c0) * TILE); g.K = (int)w;
+            g.M = (int)Mi; g.N = (int)((upd_end - c0) * TILE); g.K = (int)w;
             g.alpha = -1.0; g.beta_one = 1; g.lower = 0;
             const int64_t toff = c0 - Jend;   // the panel's digit image starts at the first row below its diagonal block
             launches += 2 + (ozaki_update_launch(g, ozs->scratch, ozs->scratch_scale,
@@ -187,11 +191,12 @@ inline int64_t trsm_fwd_t_panels(double* Xt, int64_t ldx, int64_t M, const doubl
         double* tmp = (p & 1) ? tmp1 : tmp0;
         cudaEvent_t ev_trail = (p & 1) ? ev_trail1 : ev_trail0;
         double* Xp = Xt + J * TILE * ldx;
+        Mi = tri_rows ? std::min<int64_t>(M, Jend * TILE) : M;
         // main-stream update p-2 has read tmp of this parity and brought this panel's columns up to date
         if (two && p >= 2) cudaStreamWaitEvent(panel_stream, ev_trail, 0);
         // T = Xt[:, panel] W_p^T ; the solved panel goes back into Xt (a small 2-D copy)
         gemm(tmp, M, Xp, ldx, W + p * WP * WP, WP, w, w, 1.0, 0, 1, pc);
-        cudaMemcpy2DAsync(Xp, ldx * sizeof(double), tmp, M * sizeof(double), M * sizeof(double), (size_t)w, cudaMemcpyDeviceToDevice,
+        cudaMemcpy2DAsync(Xp, ldx * sizeof(double), tmp, M * sizeof(double), Mi * sizeof(double), (size_t)w, cudaMemcpyDeviceToDevice,
                           pc.st);
         if (Jend >= upd_end) break;
         // the next panel's columns first (panel stream: its T product follows at once), everything behind them on the main stream

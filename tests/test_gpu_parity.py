@@ -75,6 +75,68 @@ def test_gemm_nt_kernel_runs_two_ctas_per_sm():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# tcgen05 trailing update (csrc/ozaki.cu): every step of it is exact except the two additions into C, so the numpy restatement
+# oracle/ozaki_model.py must be reproduced BIT FOR BIT; and the result is an f64-quality product
+@pytest.mark.parametrize("case", [(256, 128, 0, 0, False), (512, 512, 1, 0, True), (1024, 384, 1, 4, False), (1536, 512, 1, 2, True)])
+def test_tcgen05_update_is_bit_equal_to_the_integer_model(case):
+    F, N, O, *_ = _mods()
+    from oracle import ozaki_model as OM
+    M, K, lower, row_skip, scaled = case
+    rng = np.random.default_rng(M + K)
+    P = rng.standard_normal((M, K))
+    if scaled:
+        P *= np.exp2(rng.integers(-40, 40, size=(M, 1)).astype(np.float64))
+    P[M // 2 + 3] = 0.0   # an all-zero row
+    Cm = rng.standard_normal((M, M)) * 10.0
+    out = np.asfortranarray(Cm)
+    Pf = np.asfortranarray(P)
+    assert N.lib().fgp_dbg_ozaki_syrk(0, N.dptr(out), M, N.dptr(Pf), M, M, K, lower, row_skip, 0, 0, 0) == 0
+    model = OM.update(Cm, P)
+    mask = OM.launch_mask(M, lower, row_skip)
+    assert np.array_equal(out[mask], model[mask])
+    assert np.array_equal(out[~mask], Cm[~mask])
+    exact = Cm.astype(np.longdouble) - P.astype(np.longdouble) @ P.T.astype(np.longdouble)
+    rowmax = np.abs(P).max(axis=1)
+    budget = np.outer(rowmax, rowmax) * K * 2.0 ** -52 + 2.0 * np.abs(np.asarray(exact, dtype=np.float64)) * 2.0 ** -52
+    assert np.all(np.abs(np.asarray(out - exact, dtype=np.float64))[mask] <= budget[mask])
+
+
+def test_tcgen05_update_propagates_non_finite_rows():
+    F, N, O, *_ = _mods()
+    M, K = 256, 128
+    rng = np.random.default_rng(5)
+    P = np.asfortranarray(rng.standard_normal((M, K)))
+    P[7, 3] = np.nan
+    out = np.asfortranarray(rng.standard_normal((M, M)))
+    assert N.lib().fgp_dbg_ozaki_syrk(0, N.dptr(out), M, N.dptr(P), M, M, K, 0, 0, 0, 0, 0) == 0
+    assert np.all(np.isnan(out[7, :])) and np.all(np.isnan(out[:, 7]))
+    assert np.all(np.isfinite(np.delete(np.delete(out, 7, 0), 7, 1)))
+
+
+def test_fit_with_and_without_tcgen05_agree_and_meet_the_factor_tolerance():
+    """n = 4096: the first three panels' trailing updates run on tcgen05 (>= 2048 rows left), A/B against the f64 DMMA kernel
+    everywhere (FGP_OPT_TCGEN05 = 0); both within the 1e-10 factor tolerance of each other by a wide margin, same predictions."""
+    F, N, O, make_dataset, make_inputs = _mods()
+    n, d = 4096, 8
+    X, y = make_dataset(0x5EED0040, n, d)
+    Xq = make_inputs(0x5EED0041, 300, d)
+    kd = F.SquaredExp(math.sqrt(d / 6.0), 1.0).device_desc()
+    res = {}
+    for on in (1, 0):
+        h = N.Handle(0)
+        assert N.lib().fgp_set_option(h.ptr, N.FGP_OPT_TCGEN05, on) == 0
+        h.check(N.lib().fgp_fit(h.ptr, N.dptr(N.fcol(X)), n, n, d, N.dptr(y), C.byref(kd), 0.1, 0, 0.0))
+        L = np.zeros((n, n), order="F")
+        h.check(N.lib().fgp_download_factor(h.ptr, N.dptr(L), n))
+        mean, var = np.zeros(300), np.zeros(300)
+        h.check(N.lib().fgp_predict_mean_var(h.ptr, C.byref(kd), N.dptr(N.fcol(Xq)), 300, 300, N.dptr(mean), N.dptr(var)))
+        res[on] = (np.tril(L), mean, var)
+        h.close()
+    assert frob_rel(res[1][0], res[0][0]) < 1e-11   # measured 2.7e-13: two f64-accurate summation orders through a Cholesky
+    assert close(res[1][1], res[0][1]) and close(res[1][2], res[0][2])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 def test_golden_anchors_on_gpu():
     """tests/golden/anchors.json (50-digit mpmath) through the device path."""
     F, N, O, *_ = _mods()

@@ -2,7 +2,9 @@
   C3  Matern-5/2 n=16384 d=16: one scaled LML-gradient evaluation (a12+a13) and one ADAM iteration = refit + gradient (a14)
   C5  add_samples: n=16384 base + 1024 new points (a11), against a from-scratch fit of the 17408 rows
   a15 likelihood, a10 predict_covariance q=512, a16 mean pair distance
-Times are CUDA-event device times of the C-ABI calls (fgp_last_device_ms), after one warm-up call.
+Times are CUDA-event device times of the C-ABI calls (fgp_last_device_ms), after one warm-up call (buffers allocated, capacity
+grown: add_samples is timed on a model whose capacity already holds the new rows — the base model is fitted on n - k rows, a
+first add_samples of k rows grows the capacity, the SECOND one is exactly "n base + k new").
 Usage: python tools/bench_rows.py [n] [d]"""
 import json
 import math
@@ -37,6 +39,7 @@ ls = math.sqrt(d / 6.0)
 
 # ---- C3: Matern2 LML gradient -----------------------------------------------------------------------------------------
 gp = F.GaussianProcess(F.ZeroPrior(), F.Matern2(ls, 1.0), 0.1, None, X, y)
+gp._refit()
 emit("fit (Matern2)", gp._h.last_device_ms(), n ** 3 / 3.0 + float(n) * n * d)
 for rep in range(2):
     t0 = time.perf_counter()
@@ -56,12 +59,15 @@ del gp
 # ---- C5: add_samples --------------------------------------------------------------------------------------------------
 k = 1024
 Xa, ya = make_dataset(0x5EED0005, n + k, d)
-gp = F.GaussianProcess(F.ZeroPrior(), F.SquaredExp(ls, 1.0), 0.1, None, Xa[:n], ya[:n])
+gp = F.GaussianProcess(F.ZeroPrior(), F.SquaredExp(ls, 1.0), 0.1, None, Xa[:n - k], ya[:n - k])
+gp.add_samples(Xa[n - k:n], ya[n - k:n])
+emit("add_samples k=1024 onto n-k rows, first call (grows the capacity: allocations + copy of L inside)", gp._h.last_device_ms())
 gp.add_samples(Xa[n:], ya[n:])
 ms_add = gp._h.last_device_ms()
 emit("add_samples k=1024 (a11)", ms_add, float(n) * n * k + float(n) * k * k + k ** 3 / 3.0 + 2.0 * n * k * d)
 La = np.tril(gp.cholesky_factor()[n:, :][:, : n + k])  # the new block rows only (the first n rows are untouched)
 gp2 = F.GaussianProcess(F.ZeroPrior(), F.SquaredExp(ls, 1.0), 0.1, None, Xa, ya)
+gp2._refit()
 emit("from-scratch fit of n+k rows", gp2._h.last_device_ms(), (n + k) ** 3 / 3.0 + float(n + k) ** 2 * d)
 Lb = np.tril(gp2.cholesky_factor()[n:, :][:, : n + k])
 print(json.dumps({"row": "add_samples vs from-scratch: new block rows of L", "frob_rel": float(np.linalg.norm(La - Lb) /
