@@ -12,8 +12,9 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "friedrich_b200", "libfgp_sm100.so")
-PATTERNS = ["DMMA", "DFMA", "UTMALDG", "UTMASTG", "UTMAREDG", "UBLKCP", "UTMAPF", "UBLKPF", "SYNCS", "MUFU.RSQ64H", "SHFL",
-            "ATOMG", "ATOM", "RED", "LDG", "STG", "LDS", "STS", "BAR", "NANOSLEEP", "UTC", "LDTM", "STTM", "HMMA", "IMMA"]
+PATTERNS = ["UTCIMMA", "UTCBAR", "UTCATOMSWS", "LDTM", "STTM", "DMMA", "DFMA", "UTMALDG", "UTMASTG", "UTMAREDG", "UBLKCP", "UTMAPF",
+            "UBLKPF", "SYNCS", "MUFU.RSQ64H", "SHFL", "ATOMG", "ATOM", "RED", "LDG", "STG", "LDS", "STS", "BAR", "NANOSLEEP", "UTC",
+            "HMMA", "IMMA", "ELECT"]
 
 
 def main():
@@ -39,7 +40,8 @@ def main():
                 counts[cur][p] += 1
                 break
     print(f"# cuobjdump -sass {os.path.relpath(LIB, ROOT)} — opcode counts per kernel (instructions in the binary, not executed)")
-    print("# no UTC*MMA / LDTM / STTM anywhere: tcgen05 has no .kind::f64 (DESIGN.md §4); the fp64 tensor pipe is DMMA.8x8x4")
+    print("# UTCIMMA = tcgen05.mma kind::i8 (exact digit-slice products of the trailing updates, csrc/ozaki.cu), LDTM = tcgen05.ld, UTCBAR = "
+          "tcgen05.commit, UTCATOMSWS = tcgen05.alloc/dealloc; DMMA.8x8x4 = the f64 tensor pipe (tcgen05 has no .kind::f64, DESIGN.md 4)")
     tot = collections.Counter()
     for fn in order:
         c = counts[fn]
