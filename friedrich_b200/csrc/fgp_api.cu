@@ -975,15 +975,23 @@ FGP_EXPORT int fgp_add_samples(fgp_model* m, const double* Xnew, int64_t ldx, in
     const int64_t Mrows = np_new - jb * TILE;
     if (m->head_schedule) {
         const bool had_w = m->w_valid;
-        m->ozL_valid = false;   // the kept digit slices do not cover the new rows
+        // the digit slices the last full fit kept still mirror L11 (old rows x old panels): the solve of the new rows against the
+        // old columns may use them; afterwards they are stale (they do not cover the new rows)
+        const bool oz_ok = m->tcgen05 && m->ozL_valid && m->ozOffBytes.size() >= (size_t)m->pstart.size();
+        m->ozL_valid = false;
         PotrfWork w;
         int64_t p0 = 0;
         FGP_TRY(prepare_head_work(m, jb, &w, &p0));  // panel table: the old panels (the last one cut at jb), then the new ones
-        if (had_w && p0 > 0 && Mrows <= m->cap)
+        if (had_w && p0 > 0 && Mrows <= m->cap) {
+            OzPanelStore ozs{};
+            const bool use_oz = oz_ok && (int64_t)m->ozOffBytes.size() >= p0 && m->ozDigits.p;
+            if (use_oz)
+                ozs = OzPanelStore{reinterpret_cast<const int8_t*>(m->ozL.p), m->ozLscale.p, m->ozOffBytes.data(), m->ozOffRows.data(),
+                                   reinterpret_cast<int8_t*>(m->ozDigits.p), m->ozScale.p};
             m->launches += trsm_fwd_t_panels(Arows, m->cap, Mrows, m->L.p, m->cap, m->Wp.p, m->pstart.data(), p0, jb,
                                              np_new / TILE, m->pbuf[0].p, m->pbuf[1].p, m->ctx(), m->lookahead ? m->st2 : nullptr,
-                                             m->evA, m->evB, m->evC);
-        else
+                                             m->evA, m->evB, m->evC, use_oz ? &ozs : nullptr);
+        } else
             m->launches += trsm_fwd_t(Arows, m->cap, Mrows, m->L.p, m->cap, m->inv.p, 0, jb, Arows + jb * TILE * m->cap, m->ctx());
         potrf_lower_head(m->L.p, m->cap, np_new, jb, w, p0, has_eps, eps, m->info_d, m->ctx(), m->lookahead ? &la : nullptr, &cnt);
         m->w_valid = had_w;

@@ -127,7 +127,7 @@ inline int64_t trsm_fwd_t_lookahead(double* Xt, int64_t ldx, int64_t M, const do
 // Xt ARE the new block rows of L, so L[later, panel] for those columns is the panel just solved (copied back before the
 // update reads it) and the new diagonal block receives  -= T T^T  panel by panel, in order (no K = n SYRK at the end).
 // Returns the number of launches; ends joined on st.st.
-// `ozs` (optional; predict only: upd_end == i_end): digit slices of L[below, panel] kept by the fit (model.cuh ozL).  The main
+// `ozs` (optional): digit slices of L[below, panel] kept by the fit (model.cuh ozL), covering block columns < i_end.  The main
 // update of a panel that has them runs on tcgen05 (csrc/ozaki.cuh): T is sliced into the scratch image, then
 // Xt[:, later] -= T L[later, panel]^T as exact int8 products; panels without digits (fewer than OZ_MIN_ROWS rows below) and
 // the next panel's columns on the panel stream keep the f64 DMMA kernel.
@@ -168,11 +168,14 @@ inline int64_t trsm_fwd_t_panels(double* Xt, int64_t ldx, int64_t M, const doubl
     // Xt[:, block columns [c0, upd_end)] -= T L[those rows, panel p]^T on the main stream: tcgen05 when the panel's digits exist
     auto update_main = [&](int64_t p, int64_t J, int64_t Jend, int64_t c0, int64_t w, const double* tmp) {
         if (c0 >= upd_end) return;
-        if (ozs && upd_end == i_end && ozs->off_bytes[p] >= 0) {
+        const int64_t c_oz = std::min(i_end, upd_end);   // the kept digits cover the columns [.., i_end) (rows of L that existed at the fit)
+        if (ozs && ozs->off_bytes[p] >= 0 && c0 < c_oz) {
+            if (upd_end > c_oz)   // add_samples: the new block's own columns read the panel just solved (copied back): f64 DMMA
+                gemm(Xt + c_oz * TILE * ldx, ldx, tmp, M, L + c_oz * TILE + J * TILE * ldl, ldl, (upd_end - c_oz) * TILE, w, -1.0, 1, 0, st);
             ozaki_slice_launch(tmp, M, Mi, (int)w, ozs->scratch, ozs->scratch_scale, st);
             GemmArgs g{};
             g.C = Xt + c0 * TILE * ldx; g.ldc = ldx;
-            g.M = (int)Mi; g.N = (int)((upd_end - c0) * TILE); g.K = (int)w;
+            g.M = (int)Mi; g.N = (int)((c_oz - c0) * TILE); g.K = (int)w;
             g.alpha = -1.0; g.beta_one = 1; g.lower = 0;
             const int64_t toff = c0 - Jend;   // the panel's digit image starts at the first row below its diagonal block
             launches += 2 + (ozaki_update_launch(g, ozs->scratch, ozs->scratch_scale,

@@ -101,6 +101,27 @@ def test_tcgen05_update_is_bit_equal_to_the_integer_model(case):
     assert np.all(np.abs(np.asarray(out - exact, dtype=np.float64))[mask] <= budget[mask])
 
 
+def test_tcgen05_cta_pair_kernel_is_bit_equal_too():
+    """csrc/ozaki.cu ozaki_pair_kernel (cta_group::2; an experiment kept behind fgp_dbg_ozaki_experiment(32)): same integer
+    arithmetic, so the same bits — lower mode with odd column segments (lone tiles shadowed by the second CTA), row_skip, and a
+    full rectangle."""
+    F, N, O, *_ = _mods()
+    from oracle import ozaki_model as OM
+    N.lib().fgp_dbg_ozaki_experiment(32)
+    try:
+        for (M, K, lower, row_skip) in [(640, 256, 1, 0), (1152, 512, 1, 3), (384, 128, 0, 0)]:
+            rng = np.random.default_rng(M * 3 + K)
+            P = rng.standard_normal((M, K)) * np.exp2(rng.integers(-20, 20, size=(M, 1)).astype(np.float64))
+            Cm = rng.standard_normal((M, M))
+            out, Pf = np.asfortranarray(Cm), np.asfortranarray(P)
+            assert N.lib().fgp_dbg_ozaki_syrk(0, N.dptr(out), M, N.dptr(Pf), M, M, K, lower, row_skip, 0, 0, 0) == 0
+            mask = OM.launch_mask(M, lower, row_skip)
+            assert np.array_equal(out[mask], OM.update(Cm, P)[mask])
+            assert np.array_equal(out[~mask], Cm[~mask])
+    finally:
+        N.lib().fgp_dbg_ozaki_experiment(0)
+
+
 def test_tcgen05_update_propagates_non_finite_rows():
     F, N, O, *_ = _mods()
     M, K = 256, 128

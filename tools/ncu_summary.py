@@ -29,6 +29,13 @@ WANT = {
     "sm__cycles_active.avg": "sm_cycles_active",
     "smsp__inst_executed.sum": "warp_insts",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum": "smem_bank_conflicts",
+    # tcgen05 kernels (csrc/ozaki.cu): the int8 tensor sub-pipe, the SM clock the launch actually ran at (power cap), shared memory
+    "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed": "tensor_pipe_active_pct",
+    "sm__pipe_tensor_subpipe_imma_cycles_active_realtime.avg": "imma_subpipe_cycles_active",
+    "sm__cycles_elapsed.avg": "sm_cycles_elapsed",
+    "sm__cycles_elapsed.avg.per_second": "sm_clock_ghz",
+    "launch__shared_mem_per_block_dynamic": "smem_dynamic_kb",
+    "launch__cluster_size": "cluster_size",
 }
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12,
          "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0}
@@ -48,6 +55,10 @@ def main():
     for r in body:
         d = {"kernel": r[H["Kernel Name"]].split("(")[0], "grid": r[H["Grid Size"]], "block": r[H["Block Size"]]}
         for k, nm in WANT.items():
+            if k not in H:   # this ncu version prefixes some metrics with the unit they are collected in (TPC.TriageCompute. ...)
+                alt = [h for h in H if h.endswith("." + k)]
+                if alt:
+                    H[k] = H[alt[0]]
             if k in H and r[H[k]] not in ("", "n/a"):
                 v = float(r[H[k]].replace(",", ""))
                 u = units[H[k]]

@@ -79,7 +79,9 @@ def check():
 
 def bench():
     for (M, K) in [(15872, 512), (8192, 512), (4096, 512), (2048, 512), (32256, 512), (15872, 256)]:
-        for tpc in (2, 4):
+        if M == 32256 and len(sys.argv) > 2:
+            continue
+        for tpc in (0, 1, 2):
             mu, msl = C.c_double(0), C.c_double(0)
             rc = lib.fgp_dbg_ozaki_bench(0, M, K, 5, tpc, C.byref(mu), C.byref(msl))
             tiles = (M // 128) * (M // 128 + 1) // 2
@@ -94,18 +96,22 @@ def bench():
 
 def experiments():
     """which part bounds the update kernel: the same launch with parts switched off"""
+    base = 32 if (len(sys.argv) > 2 and sys.argv[2] == "pairs") else 0
     for flags, what in [(0, "production"), (1, "no epilogue"), (2, "no operand copies"), (3, "MMAs only"), (4, "no MMAs"),
-                        (5, "copies only"), (6, "epilogue only"), (11, "MMAs only, N=256 probe (18 per k-step)")]:
-        lib.fgp_dbg_ozaki_experiment(flags)
+                        (5, "copies only"), (6, "epilogue only")]:
+        lib.fgp_dbg_ozaki_experiment(flags | base)
         mu = C.c_double(0)
-        rc = lib.fgp_dbg_ozaki_bench(0, 15872, 512, 3, 2, C.byref(mu), None)
-        print(json.dumps({"experiment": what, "flags": flags, "rc": rc, "update_ms": mu.value, "us_per_tile": mu.value * 148 / 7750 * 1e3}), flush=True)
+        rc = lib.fgp_dbg_ozaki_bench(0, 15872, 512, 3, 0 if base else 2, C.byref(mu), None)
+        print(json.dumps({"experiment": what, "pairs": bool(base), "flags": flags, "rc": rc, "update_ms": mu.value, "us_per_tile": mu.value * 148 / 7750 * 1e3}), flush=True)
     lib.fgp_dbg_ozaki_experiment(0)
 
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     good = True
+    if what == "pairs":   # the CTA-pair kernel (cta_group::2): same checks, then the timings
+        lib.fgp_dbg_ozaki_experiment(32)
+        what = "all"
     if what in ("check", "all"):
         good = check()
         print("CHECK", "OK" if good else "FAILED", flush=True)
