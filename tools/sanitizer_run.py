@@ -1,5 +1,7 @@
 """Small end-to-end run for compute-sanitizer (memcheck / racecheck / synccheck): the head kernel alone on 1..4 tiles, a fit
-through the head schedule (two panels + a partial one), predict (batched and latency paths), add_samples, LML gradient."""
+through the head schedule (two panels + a partial one), predict (batched and latency paths), add_samples, LML gradient; the
+tcgen05 update kernel and its digit slicing alone (single-CTA and CTA-pair kernels) and inside a fit + predict + LML gradient
+large enough to route through them (n = 2560: 2048 rows below the first panel)."""
 import ctypes as C
 import sys
 
@@ -29,3 +31,21 @@ gp.add_samples(X[1000:], y[1000:])
 s, g = gp.scaled_gradient_marginal_likelihood()
 cov = gp.predict_covariance(Xq[:40])
 print("ok", float(m[0]), float(v2[0]), s, g, float(cov[0, 0]))
+
+# tcgen05 path
+rng = np.random.default_rng(9)
+for flags in (0, 32):
+    N.lib().fgp_dbg_ozaki_experiment(flags)
+    for (M, K, lower, skip) in [(384, 256, 1, 0), (256, 128, 0, 0), (640, 512, 1, 2)]:
+        P = np.asfortranarray(rng.standard_normal((M, K)))
+        Cm = np.asfortranarray(rng.standard_normal((M, M)))
+        rc = N.lib().fgp_dbg_ozaki_syrk(0, N.dptr(Cm), M, N.dptr(P), M, M, K, lower, skip, 0, 0, 0)
+        print("ozaki", "pairs" if flags else "single", M, K, lower, skip, "rc", rc)
+N.lib().fgp_dbg_ozaki_experiment(0)
+if "--small" not in sys.argv:
+    n2 = 2560
+    X2, y2 = make_dataset(5, n2, d)
+    gp2 = F.GaussianProcess(F.ZeroPrior(), F.SquaredExp(0.8, 1.0), 0.1, None, X2, y2)
+    m3, v3 = gp2.predict_mean_variance(Xq)
+    s2, g2 = gp2.scaled_gradient_marginal_likelihood()
+    print("ok tcgen05 fit", float(m3[0]), float(v3[0]), s2, g2)
