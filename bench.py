@@ -206,7 +206,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "gp_fit_tflops", "value": val, "unit": "TFLOP/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak" if args.workload == "metric" else "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+        "vs_baseline": None, "dtype": "f64",
+        "dtype_detail": "inputs, outputs and storage f64; O(n^3) trailing updates / solve updates computed as exact int8 x int8 -> int32 "
+                        "digit-slice products on tcgen05 (36 per f64 product, two f64 roundings per element and launch), panel chain "
+                        "in f64 on the DMMA pipe; same tolerances as a pure f64 path (tests/test_gpu_parity.py)", "data": "synthetic", "config": config,
         "sample": {"n": ns, "q": qs, "d": d, "what": sample},
         "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": 1, "kind": "port", "sample": sample,
                          "fit_seconds_by_n": rows, "fitted_exponent": p,
@@ -537,6 +540,9 @@ def run_ours(args, rank, local_rank, world):
         # whose N = 1 point is the metric's own configuration; the strong-scaling experiment of the north star (C4) is the
         # `strong_c4` block of every N > 1 line
         "scaling": "weak" if args.workload == "metric" else "strong", "vs_baseline": None, "dtype": "f64",
+        "dtype_detail": "inputs, outputs and storage f64; O(n^3) trailing updates / solve updates computed as exact int8 x int8 -> int32 "
+                        "digit-slice products on tcgen05 (36 per f64 product, two f64 roundings per element and launch), panel chain "
+                        "in f64 on the DMMA pipe; same tolerances as a pure f64 path (tests/test_gpu_parity.py)",
         "data": "synthetic", "config": config,
         "frac_of_fp64_peak": value / (world * FP64_PEAK_TFLOPS),
         "predict_qps": q / (pred_ms * 1e-3), "predict_ms": pred_ms, "predict_q1_latency_ms": q1_ms,
