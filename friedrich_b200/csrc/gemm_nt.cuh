@@ -97,6 +97,9 @@ __host__ __device__ inline void gemm_tile_decode(const GemmArgs& g, int b, int& 
     if (!g.lower) {
         ti = b % tm;
         tj = b / tm;
+        // A W^T with block-triangular W: tile column j contracts over 128 (j + 1) columns — heaviest tile columns first, so that
+        // the last wave of the launch is made of the light ones
+        if (g.k_upto_col) tj = g.N / GEMM_BN - 1 - tj;
         return;
     }
     const int PT = g.grp > 0 ? g.grp : 1, S = g.stride > 0 ? g.stride : 1, tn = g.N / GEMM_BN, R = g.band_rows;

@@ -744,8 +744,21 @@ int64_t ozaki_update_launch(const GemmArgs& g, const int8_t* digitsA, const doub
     o.KS = g.K / OZ_KSTEP;
     o.tiles = (int)tiles;
     const int num_sms = gemm_nt_num_sms();
+    // tiles per CTA: CTAs are dispatched in waves of one per SM, so the launch lasts about waves x (tpc tiles + set-up); pick the
+    // tpc <= 4 (longer-lived CTAs hold back the panel stream: measured, fit 28.8 -> 29.2 ms with up to 8) with the shortest estimate (measured per-tile / per-CTA times; M = 4096: 528 tiles -> 4 per CTA = one wave,
+    // 0.138 ms against 0.196 ms with 3), ties to the smaller one so that CTAs retire early for the panel stream
     int tpc = tiles_per_cta;
-    if (tpc <= 0) tpc = (int)std::max<int64_t>(1, std::min<int64_t>(4, tiles / (2 * num_sms)));
+    if (tpc <= 0) {
+        double best = 0.0;
+        for (int c = 1; c <= 4; ++c) {
+            const int64_t ctas = (tiles + c - 1) / c, waves = (ctas + num_sms - 1) / num_sms;
+            const double est = (double)waves * (34.0 * c + 3.0);
+            if (c == 1 || est < best * 0.995) {
+                best = est;
+                tpc = c;
+            }
+        }
+    }
     o.tpc = tpc;
     o.lbo = lbo; o.sbo = sbo;
     o.exp = g_oz_exp;

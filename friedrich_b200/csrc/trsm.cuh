@@ -206,6 +206,9 @@ inline int64_t trsm_fwd_t_panels(double* Xt, int64_t ldx, int64_t M, const doubl
         const int64_t Jnext = (Jend < i_end) ? pend(p + 1) : Jend;
         if (two) {
             cudaEventRecord(ev_panel, panel_stream);
+            // the next panel's columns also receive the main-stream update of panel p-1 (they lie behind ITS next panel): wait for
+            // it, so that every element gets its additions in panel order whatever the timing (results reproducible bit for bit)
+            if (p >= 1) cudaStreamWaitEvent(panel_stream, (p & 1) ? ev_trail0 : ev_trail1, 0);
             gemm(Xt + Jend * TILE * ldx, ldx, tmp, M, L + Jend * TILE + J * TILE * ldl, ldl, (Jnext - Jend) * TILE, w, -1.0, 1, 0, pc);
             cudaStreamWaitEvent(st.st, ev_panel, 0);
             update_main(p, J, Jend, Jnext, w, tmp);

@@ -81,7 +81,7 @@ def bench():
     for (M, K) in [(15872, 512), (8192, 512), (4096, 512), (2048, 512), (32256, 512), (15872, 256)]:
         if M == 32256 and len(sys.argv) > 2:
             continue
-        for tpc in (0, 1, 2):
+        for tpc in (1, 2, 3, 4, 6):
             mu, msl = C.c_double(0), C.c_double(0)
             rc = lib.fgp_dbg_ozaki_bench(0, M, K, 5, tpc, C.byref(mu), C.byref(msl))
             tiles = (M // 128) * (M // 128 + 1) // 2
