@@ -114,8 +114,8 @@ int prepare_head_work(fgp_model* m, int64_t jb_begin, PotrfWork* w, int64_t* p0)
         w->oz_digits = reinterpret_cast<int8_t*>(m->ozDigits.p);
         w->oz_scale = m->ozScale.p;
         m->ozL_valid = false;
-        if (jb_begin == 0 && !m->comm) {
-            // full single-GPU fit: every panel with >= OZ_MIN_ROWS rows below it keeps its digit slices (8 bytes per element of
+        if (jb_begin == 0) {
+            // full fit (single GPU, or sharded: every rank slices every received panel): every panel with >= OZ_MIN_ROWS rows below it keeps its digit slices (8 bytes per element of
             // L below the panel's diagonal block: as many bytes as that part of L) for the solves of predict
             m->ozOffBytes.assign((size_t)slots, -1);
             m->ozOffRows.assign((size_t)slots, -1);
@@ -1164,8 +1164,15 @@ int run_factor_sharded(fgp_model* m, const fgp_kernel_desc* kernel, const Kernel
     PotrfWork w;
     int64_t p0 = 0;
     FGP_TRY(prepare_head_work(m, 0, &w, &p0));
-    m->w_valid = false;  // a rank only holds the inverse blocks of the panels it owns
-    return factor_sharded_head(m, kernel, kt, noise, has_eps, eps, w);
+    m->w_valid = false;
+    const int rc = factor_sharded_head(m, kernel, kt, noise, has_eps, eps, w);
+    if (rc == FGP_OK) {
+        // every rank ends with the full factor, every panel's inverse diagonal block W_p (broadcast beside the panel) and the digit
+        // slices of every panel: predict / likelihood / LML gradient run locally like after a single-GPU fit
+        m->w_valid = true;
+        m->ozL_valid = w.oz_off_bytes != nullptr;
+    }
+    return rc;
 }
 
 int finish_sharded(fgp_model* m, int rc) {

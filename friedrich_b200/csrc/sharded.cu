@@ -255,6 +255,9 @@ int factor_sharded_head(fgp_model* m, const fgp_kernel_desc* kd, const KernelTra
         cnt.launches += gemm_nt_launch(g, c) > 0;
     };
     bool copy_pending[2] = {false, false};
+    // digit slices of panel q: kept per panel when the model holds a store for them (prepare_head_work), else one scratch image
+    auto oz_dig = [&](int64_t q) { return w.oz_digits + ((w.oz_off_bytes && w.oz_off_bytes[q] >= 0) ? w.oz_off_bytes[q] : 0); };
+    auto oz_sc = [&](int64_t q) { return w.oz_scale + ((w.oz_off_rows && w.oz_off_rows[q] >= 0) ? w.oz_off_rows[q] : 0); };
     for (int64_t p = 0; p < NP; ++p) {
         const int64_t J = p * PT, Jend = std::min<int64_t>(J + PT, nb);
         const int64_t rows = np - J * TILE, wc = (Jend - J) * TILE, below = rows - wc;
@@ -288,8 +291,8 @@ int factor_sharded_head(fgp_model* m, const fgp_kernel_desc* kd, const KernelTra
                         g.M = (int)below; g.N = (int)wc; g.K = (int)wp;
                         g.alpha = -1.0; g.beta_one = 1; g.lower = 0;
                         const int KS = (int)(wp / OZ_KSTEP);
-                        cnt.launches += ozaki_update_launch(g, w.oz_digits + (Jend - J) * (int64_t)KS * OZ_PART_BYTES, w.oz_scale + (Jend - J) * TILE,
-                                                            w.oz_digits, w.oz_scale, 0, sc) > 0;
+                        cnt.launches += ozaki_update_launch(g, oz_dig(p - 1) + (Jend - J) * (int64_t)KS * OZ_PART_BYTES, oz_sc(p - 1) + (Jend - J) * TILE,
+                                                            oz_dig(p - 1), oz_sc(p - 1), 0, sc) > 0;
                     } else {
                         gemm(A21, m->cap, prev + (Jend - Jp) * TILE, rows_p, mine, rows_p, below, wc, wp, -1.0, 1, 0, 0, sc);
                     }
@@ -324,6 +327,11 @@ int factor_sharded_head(fgp_model* m, const fgp_kernel_desc* kd, const KernelTra
             ProfScope ps(bc, PROF_OTHER, (double)rows * wc * sizeof(double));
             NC(m, nccl->Broadcast(buf, buf, (size_t)rows * wc, ncclDouble, owner, cm->comm, cm->st_comm));
             cm->bcast_bytes += (double)rows * wc * sizeof(double);
+            // the panel's inverse diagonal block W_p = L11^-1 (2 MB) follows: with it every rank can run the panel solves of
+            // predict and of the LML gradient locally (trsm.cuh), like after a single-GPU fit
+            double* Wp = w.W + p * HEAD_PANEL * HEAD_PANEL;
+            NC(m, nccl->Broadcast(Wp, Wp, (size_t)HEAD_PANEL * HEAD_PANEL, ncclDouble, owner, cm->comm, cm->st_comm));
+            cm->bcast_bytes += (double)HEAD_PANEL * HEAD_PANEL * sizeof(double);
         }
         CU(m, cudaEventRecord(cm->ev_bcast, cm->st_comm));
         CU(m, cudaStreamWaitEvent(m->st2, cm->ev_bcast, 0));  // the next owner's look-ahead reads the buffer on st2 / st3
@@ -332,7 +340,7 @@ int factor_sharded_head(fgp_model* m, const fgp_kernel_desc* kd, const KernelTra
         // diagonal block into base-128 digits (tile 0 of the digit buffer = first row below the panel)
         const bool oz = w.oz_digits && below >= OZ_MIN_ROWS;
         if (oz) {
-            ozaki_slice_launch(buf + wc, rows, below, (int)wc, w.oz_digits, w.oz_scale, mc);
+            ozaki_slice_launch(buf + wc, rows, below, (int)wc, oz_dig(p), oz_sc(p), mc);
             cnt.launches += 2;
             CU(m, cudaEventRecord(m->evD, m->st));
         }
@@ -353,8 +361,8 @@ int factor_sharded_head(fgp_model* m, const fgp_kernel_desc* kd, const KernelTra
                 g.grp = (int)PT; g.stride = (int)(P * PT);
                 if (oz) {
                     const int64_t toff = c0 - Jend;   // C's origin in tiles below the panel
-                    const int8_t* dg = w.oz_digits + toff * (wc / OZ_KSTEP) * (int64_t)OZ_PART_BYTES;
-                    cnt.launches += ozaki_update_launch(g, dg, w.oz_scale + toff * TILE, dg, w.oz_scale + toff * TILE, 0, mc) > 0;
+                    const int8_t* dg = oz_dig(p) + toff * (wc / OZ_KSTEP) * (int64_t)OZ_PART_BYTES;
+                    cnt.launches += ozaki_update_launch(g, dg, oz_sc(p) + toff * TILE, dg, oz_sc(p) + toff * TILE, 0, mc) > 0;
                 } else {
                     cnt.launches += gemm_nt_launch(g, mc) > 0;
                 }
