@@ -460,7 +460,7 @@ FGP_EXPORT int fgp_destroy(fgp_model* m) {
         for (DevBuf* b : {&m->xr, &m->xc, &m->nc, &m->nr, &m->cmean, &m->y, &m->z, &m->alpha, &m->work, &m->L, &m->inv,
                           &m->invT, &m->staging, &m->qr, &m->qc, &m->qnc, &m->qnr, &m->bt, &m->partial, &m->mean_d,
                           &m->var_d, &m->scalars, &m->kqq, &m->U, &m->Kinv, &m->lml_partial, &m->lml_rows, &m->Wp, &m->Pscr, &m->pbuf[0],
-                          &m->pbuf[1]})
+                          &m->pbuf[1], &m->ozDigits, &m->ozScale, &m->ozL, &m->ozLscale, &m->ozU})
             b->release();
         if (m->head_sync) cudaFree(m->head_sync);
         for (cudaEvent_t e : {m->evTop, m->evRest, m->evCopy[0], m->evCopy[1]})
