@@ -114,6 +114,7 @@ SIGNATURES = {
                                   C.c_int, C.c_int]),
     "fgp_dbg_ozaki_syrk": (C.c_int, [C.c_int, _dp, _i64, _dp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int]),
+    "fgp_linear_prior_fit": (C.c_int, [_h, _dp, _dp, _dp]),
     "fgp_dbg_ozaki_experiment": (None, [C.c_int]),
     "fgp_dbg_ozaki_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp]),
 }

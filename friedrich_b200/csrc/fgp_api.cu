@@ -779,6 +779,19 @@ FGP_EXPORT int fgp_mean_pair_distance(fgp_model* m, double* out) {
     return rc != FGP_OK ? rc : rc2;
 }
 
+FGP_EXPORT int fgp_linear_prior_fit(fgp_model* m, const double* y, double* weights, double* intercept) {
+    if (!m) return FGP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (m->n <= 0) return fail(m, FGP_ERR_NOT_FITTED, "no resident training set");
+    if (!y || !weights || !intercept) return fail(m, FGP_ERR_BAD_ARG, "null argument");
+    begin_timed(m);
+    int rc = linear_prior_fit_device(m, y, weights, intercept);
+    if (rc == FGP_ERR_BAD_ARG) rc = fail(m, FGP_ERR_BAD_ARG, "linear prior fit supports up to 44 input dimensions");
+    int rc2 = end_timed(m);
+    return rc != FGP_OK ? rc : rc2;
+}
+
 // =================================================================================================================
 // state transfer
 FGP_EXPORT int fgp_download_factor(fgp_model* m, double* L, int64_t ldl) {

@@ -1,5 +1,8 @@
 // lml.cu — LML-gradient reductions and the bandwidth heuristic on the pair-tile engine (contract in lml.cuh).
 #include "lml.cuh"
+
+#include <cmath>
+#include <vector>
 #include "ozaki.cuh"
 #include "potrf.cuh"
 #include "trsm.cuh"
@@ -357,6 +360,113 @@ int mean_pair_distance_device(fgp_model* m, double* out) {
     CU(m, cudaStreamSynchronize(m->st));
     const double n = (double)m->n;
     *out = m->pinned[0] / ((n * n - n) / 2.0);  // kernel.rs:111-112
+    return FGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// LinearPrior::fit (src/parameters/prior.rs:139-159: least squares of y on [1 | X]).  On the CENTRED resident points Xc the
+// intercept decouples (the columns of Xc sum to zero): slopes w solve (Xc^T Xc) w = Xc^T y, intercept = mean(y) - mean(X).w.
+// One kernel accumulates, per block of rows, the d x (d + 2) table [Xc^T Xc | Xc^T y | .] and sum(y); partials are summed in a
+// fixed order (deterministic); the d x d system is solved on the host (the reference's SVD solve is host code too).
+__global__ void __launch_bounds__(256) prior_normal_kernel(const double* __restrict__ xc, int dp, int d, const double* __restrict__ y,
+                                                           int64_t n, int64_t rows_per_block, double* __restrict__ partial) {
+    extern __shared__ double sm[];   // [256][d + 1]: centred point, y
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(n, r0 + rows_per_block);
+    const int W = d + 1, nout = d * W + 1;
+    double acc[8];   // this thread's outputs t = threadIdx.x + 256 k (nout <= 8 * 256)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+    for (int64_t c0 = r0; c0 < r1; c0 += 256) {
+        const int64_t r = c0 + threadIdx.x;
+        if (r < r1) {
+            for (int j = 0; j < d; ++j) sm[threadIdx.x * W + j] = xc[r * dp + j];
+            sm[threadIdx.x * W + d] = y[r];
+        } else {
+            for (int j = 0; j <= d; ++j) sm[threadIdx.x * W + j] = 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int t = threadIdx.x + 256 * k;
+            if (t < nout) {
+                double a = acc[k];
+                if (t == nout - 1) {
+                    for (int q = 0; q < 256; ++q) a += sm[q * W + d];                       // sum(y)
+                } else {
+                    const int i = t / W, j = t % W;                                          // j == d: Xc^T y
+                    for (int q = 0; q < 256; ++q) a = fma(sm[q * W + i], sm[q * W + j], a);
+                }
+                acc[k] = a;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int t = threadIdx.x + 256 * k;
+        if (t < nout) partial[(int64_t)blockIdx.x * nout + t] = acc[k];
+    }
+}
+__global__ void prior_normal_final_kernel(const double* __restrict__ partial, int blocks, int nout, double* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nout) return;
+    double a = 0.0;
+    for (int b = 0; b < blocks; ++b) a += partial[(int64_t)b * nout + t];
+    out[t] = a;
+}
+
+int linear_prior_fit_device(fgp_model* m, const double* y_host, double* weights, double* intercept) {
+    const int d = (int)m->d, W = d + 1, nout = d * W + 1;
+    if (nout > 8 * 256) return FGP_ERR_BAD_ARG;   // d <= 44
+    const int64_t n = m->n, rpb = 2048;
+    const int blocks = (int)((n + rpb - 1) / rpb);
+    CU(m, m->work.reserve((size_t)std::max<int64_t>(m->cap, n)));
+    CU(m, cudaMemcpyAsync(m->work.p, y_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, m->st));
+    CU(m, m->lml_partial.reserve((size_t)blocks * nout + nout + d));
+    double* out = m->lml_partial.p + (size_t)blocks * nout;
+    const size_t smem = (size_t)256 * W * sizeof(double);
+    if (smem > 48 * 1024) CU(m, cudaFuncSetAttribute(prior_normal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prior_normal_kernel<<<blocks, 256, smem, m->st>>>(m->xc.p, (int)m->dp, d, m->work.p, n, rpb, m->lml_partial.p);
+    prior_normal_final_kernel<<<(nout + 127) / 128, 128, 0, m->st>>>(m->lml_partial.p, blocks, nout, out);
+    m->launches += 2;
+    CU(m, cudaMemcpyAsync(out + nout, m->cmean.p, (size_t)d * sizeof(double), cudaMemcpyDeviceToDevice, m->st));
+    FGP_TRY(ensure_pinned(m, (size_t)nout + d));
+    CU(m, cudaMemcpyAsync(m->pinned, out, (size_t)(nout + d) * sizeof(double), cudaMemcpyDeviceToHost, m->st));
+    CU(m, cudaStreamSynchronize(m->st));
+    // host: Cholesky of the d x d normal matrix G (row i of the table: G[i][0..d), then (Xc^T y)[i])
+    std::vector<double> G((size_t)d * d), b((size_t)d);
+    for (int i = 0; i < d; ++i) {
+        for (int j = 0; j < d; ++j) G[(size_t)i * d + j] = m->pinned[i * W + j];
+        b[i] = m->pinned[i * W + d];
+    }
+    for (int j = 0; j < d; ++j) {
+        double s = G[(size_t)j * d + j];
+        for (int k = 0; k < j; ++k) s -= G[(size_t)j * d + k] * G[(size_t)j * d + k];
+        if (!(s > 0.0)) return fail(m, FGP_ERR_NOT_POSDEF, "linear prior fit: the centred inputs are rank deficient");
+        const double ljj = std::sqrt(s);
+        G[(size_t)j * d + j] = ljj;
+        for (int i = j + 1; i < d; ++i) {
+            double t = G[(size_t)i * d + j];
+            for (int k = 0; k < j; ++k) t -= G[(size_t)i * d + k] * G[(size_t)j * d + k];
+            G[(size_t)i * d + j] = t / ljj;
+        }
+    }
+    for (int i = 0; i < d; ++i) {   // L z = b
+        double t = b[i];
+        for (int k = 0; k < i; ++k) t -= G[(size_t)i * d + k] * b[k];
+        b[i] = t / G[(size_t)i * d + i];
+    }
+    for (int i = d - 1; i >= 0; --i) {   // L^T w = z
+        double t = b[i];
+        for (int k = i + 1; k < d; ++k) t -= G[(size_t)k * d + i] * b[k];
+        b[i] = t / G[(size_t)i * d + i];
+    }
+    double c = m->pinned[nout - 1] / (double)n;   // mean(y)
+    for (int i = 0; i < d; ++i) {
+        weights[i] = b[i];
+        c -= m->pinned[nout + i] * b[i];          // - mean(X) . w
+    }
+    *intercept = c;
     return FGP_OK;
 }
 

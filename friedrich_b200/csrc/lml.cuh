@@ -33,4 +33,7 @@ int mean_pair_distance_device(fgp_model* m, double* out);
 // A[i + i*ld] = 1 for i < n
 void launch_set_identity(double* A, int64_t ld, int64_t n, cudaStream_t st);
 
+// LinearPrior::fit on the resident (centred) training inputs; y_host = the ORIGINAL outputs (n values)
+int linear_prior_fit_device(fgp_model* m, const double* y_host, double* weights, double* intercept);
+
 }  // namespace fgp

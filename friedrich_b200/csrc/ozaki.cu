@@ -727,6 +727,13 @@ int64_t ozaki_update_launch(const GemmArgs& g, const int8_t* digitsA, const doub
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
     const int64_t tiles = gemm_nt_tiles(g);
     if (tiles <= 0) return 0;
+    // contract: whole tiles / k-steps, int32-exact contraction length, alpha = +-1 (anything else would need a rounding)
+    if (g.M % GEMM_BM || g.N % GEMM_BN || g.K % OZ_KSTEP || g.K > 32768 || (g.alpha != 1.0 && g.alpha != -1.0) || !g.beta_one ||
+        g.k_upto_col) {
+        fprintf(stderr, "libfgp_sm100: ozaki_update_launch: unsupported problem (M=%d N=%d K=%d alpha=%g)\n", g.M, g.N, g.K, g.alpha);
+        gemm_nt_flag_error();
+        return 0;
+    }
     if (ozaki_prepare() != cudaSuccess) {
         gemm_nt_flag_error();
         return 0;

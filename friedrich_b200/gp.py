@@ -352,7 +352,15 @@ class GaussianProcess:
         if fit_prior:
             X, y_resid = self._X_host, self._y_host
             y_raw = y_resid + self.prior.prior(X)                 # mod.rs:415
-            self.prior.fit(X, y_raw)                               # mod.rs:417
+            if isinstance(self.prior, LinearPrior) and X.shape[1] <= 44:
+                # prior.rs:139-159 on the resident inputs (fgp_linear_prior_fit): normal equations on the device, d x d solve
+                w = np.zeros(X.shape[1])
+                b = C.c_double(0.0)
+                self._h.check(N.lib().fgp_linear_prior_fit(self._h.ptr, N.dptr(np.ascontiguousarray(y_raw)), N.dptr(w),
+                                                           C.cast(C.byref(b), N._dp)))
+                self.prior.weights, self.prior.intercept = w, b.value
+            else:
+                self.prior.fit(X, y_raw)                           # mod.rs:417
             y_resid = np.ascontiguousarray(y_raw - self.prior.prior(X))   # mod.rs:419-420
             self._y_host = y_resid
             self._h.check(N.lib().fgp_set_outputs(self._h.ptr, N.dptr(y_resid), len(y_resid)))

@@ -181,6 +181,11 @@ int fgp_set_profiling(fgp_model* m, int on);
 enum fgp_option { FGP_OPT_LOOKAHEAD = 1, FGP_OPT_HEAD = 2, FGP_OPT_TCGEN05 = 3 };
 int fgp_set_option(fgp_model* m, int option, int64_t value);
 int fgp_profile_summary(const fgp_model* m, double* ms, double* flops, int64_t* count);
+/* LinearPrior::fit (src/parameters/prior.rs:139-159): least squares of the ORIGINAL outputs y (n values, host) on [1 | X] for the
+ * resident training inputs. The normal equations are accumulated on the device over the centred inputs (the intercept
+ * decouples), the d x d system is solved on the host; weights: d values. FGP_ERR_NOT_POSDEF when the inputs are rank deficient
+ * (the reference's SVD solve would return a minimum-norm answer there); d <= 44. */
+int fgp_linear_prior_fit(fgp_model* m, const double* y, double* weights, double* intercept);
 /* Resident-input predict for kernel-only timing: stage queries once, then run the device part repeatedly. */
 int fgp_stage_queries(fgp_model* m, const double* Xq, int64_t ldq, int64_t q);
 int fgp_predict_staged(fgp_model* m, const fgp_kernel_desc* kernel, int want_mean, int want_var);

@@ -436,6 +436,30 @@ def test_builder_train_with_parameter_fit_follows_oracle_trajectory():
     assert close(gp.predict(Xq), ref.predict(Xq), rtol=1e-7, atol=1e-9)
 
 
+@pytest.mark.parametrize("shape", [(5000, 6), (1300, 17), (3000, 40)])
+def test_linear_prior_fit_on_device_matches_least_squares(shape):
+    """prior.rs:139-159 through fgp_linear_prior_fit (normal equations on the resident centred inputs) and through
+    fit_parameters(fit_prior=True) of a LinearPrior model, against the oracle's SVD least squares."""
+    F, N, O, make_dataset, make_inputs = _mods()
+    n, d = shape
+    X, y = make_dataset(0x5EED0050 + d, n, d)
+    rng = np.random.default_rng(d)
+    y = y + X @ rng.standard_normal(d) * 3.0 + 1.7
+    ref = O.LinearPrior.default(d)
+    ref.fit(X, y)
+    gp = F.GaussianProcess(F.LinearPrior.default(d), F.SquaredExp(math.sqrt(d / 6.0), 1.0), 0.1, None, X, y)
+    w, b = np.zeros(d), C.c_double(0.0)
+    gp._h.check(N.lib().fgp_linear_prior_fit(gp._h.ptr, N.dptr(y), N.dptr(w), C.cast(C.byref(b), N._dp)))
+    assert np.allclose(w, ref.weights, rtol=1e-9, atol=1e-11) and abs(b.value - ref.intercept) < 1e-9 * max(1.0, abs(ref.intercept))
+    gp.fit_parameters(True, False)
+    assert np.allclose(gp.prior.weights, ref.weights, rtol=1e-9, atol=1e-11)
+    assert abs(gp.prior.intercept - ref.intercept) < 1e-9 * max(1.0, abs(ref.intercept))
+    if n <= 1500:
+        oref = O.OracleGaussianProcess(ref, O.KernelDesc.make([O.K_SQUARED_EXP], [math.sqrt(d / 6.0), 1.0]), 0.1, None, X, y)
+        Xq = make_inputs(99, 50, d)
+        assert close(gp.predict(Xq), oref.predict(Xq), rtol=1e-7, atol=1e-9)
+
+
 def test_unscaled_optimizer_trajectory():
     """optimizer.rs:69-149 (non-scalable kernel: noise fitted in log space)."""
     F, N, O, make_dataset, make_inputs = _mods()
