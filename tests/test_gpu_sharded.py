@@ -52,6 +52,32 @@ def test_single_rank_sharded_fit_matches_oracle_and_plain_fit(n, d):
     assert np.array_equal(np.tril(_factor(N, hs, n)), np.tril(_factor(N, hp, n)))
 
 
+def test_single_rank_sharded_fit_on_the_tcgen05_path_is_bitwise_equal_and_predicts_alike():
+    """n = 4608: the first five panels have >= 2048 rows below them, so the sharded schedule's look-ahead update of the next
+    panel's column block and its grouped trailing update run on tcgen05 (csrc/ozaki.cu) — same per-tile arithmetic as the
+    single-GPU schedule, hence the same bits; the sharded fit also keeps the digit slices and every W_p, so predict takes the
+    tcgen05 panel solve afterwards and must reproduce the plain model's predictions bit for bit."""
+    N, sharded, SquaredExp, Matern2, make_dataset, O = _mods()
+    from friedrich_b200.synthetic import make_inputs
+    n, d, q = 4608, 6, 300
+    X, y = make_dataset(4000 + n, n, d)
+    Xq = make_inputs(4001 + n, q, d)
+    kd = SquaredExp(math.sqrt(d / 6.0), 1.0).device_desc()
+    hs, hp = N.Handle(0), N.Handle(0)
+    sharded.comm_init(hs, 0, 1)
+    sharded.fit_sharded(hs, X, y, kd, 0.1)
+    hp.check(N.lib().fgp_fit(hp.ptr, N.dptr(N.fcol(X)), n, n, d, N.dptr(y), C.byref(kd), 0.1, 0, 0.0))
+    assert np.array_equal(np.tril(_factor(N, hs, n)), np.tril(_factor(N, hp, n)))
+    out = {}
+    for name, h in (("sharded", hs), ("plain", hp)):
+        mean, var = np.zeros(q), np.zeros(q)
+        h.check(N.lib().fgp_predict_mean_var(h.ptr, C.byref(kd), N.dptr(N.fcol(Xq)), q, q, N.dptr(mean), N.dptr(var)))
+        out[name] = (mean, var)
+    assert np.array_equal(out["sharded"][0], out["plain"][0]) and np.array_equal(out["sharded"][1], out["plain"][1])
+    hs.close()
+    hp.close()
+
+
 def test_sharded_fit_reports_failing_column():
     N, sharded, SquaredExp, Matern2, make_dataset, O = _mods()
     n, d = 700, 2
