@@ -235,7 +235,7 @@ def workload_config(workload, world, use_sharded, lookahead=True):
                      "multi_gpu": ("block-cyclic 512-column panels, NCCL panel broadcast, replicated factor; queries sharded")
                      if use_sharded else "single GPU", "lookahead": lookahead,
                      "trailing_updates": "tcgen05.mma kind::i8 on exact base-128 digit slices (8 slices, 36 products, int32 TMEM "
-                                         "accumulators) while >= 2048 rows are left, f64 DMMA below; results are f64"}
+                                         "accumulators) while >= 1024 rows are left, f64 DMMA below; results are f64"}
 
 
 def weak_n(world):
@@ -504,7 +504,7 @@ def run_ours(args, rank, local_rank, world):
     dmma_block = {"kernel": "gemm_nt_kernel", "bound": "tensor", "achieved": gemm_tflops, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                   "frac": (gemm_tflops / FP64_PEAK_TFLOPS) if gemm_tflops else None, "launches": int(tcnt[0]),
                   "share_of_step": float(tms[0] / max(prof_dev_ms, 1e-9)), "isolated": iso,
-                  "what": "f64 DMMA kernel: panel solves A21 W^T, next-diagonal-block updates, trailing updates with < 2048 rows left",
+                  "what": "f64 DMMA kernel: panel solves A21 W^T, next-diagonal-block updates, trailing updates with < 1024 rows left",
                   "peak_source": "fp64 DMMA m8n8k4 register-resident burst measured on this pool (profiles/fp64_peak_r01.jsonl; "
                                  "MEASURED_PEAKS.json has no fp64 figure; nominal 148 SM x 128 flop/clk x 1.965 GHz = 37.2)"}
     if tc_f64 is not None and tms[4] >= tms[0]:

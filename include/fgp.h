@@ -175,7 +175,7 @@ int fgp_set_profiling(fgp_model* m, int on);
 /* FGP_OPT_HEAD (default 1): factor each 512-column panel's diagonal block and its inverse in ONE multi-CTA launch
  * (csrc/potrf_head.cu) and solve everything below it as one K <= 512 GEMM; 0 = the per-block-column schedule
  * (diagonal tile / panel solve / rank-128 update launch triples). Results agree to rounding, not bit for bit. */
-/* FGP_OPT_TCGEN05 (default 1): trailing updates behind a panel with at least 2048 rows left run on the 5th-generation
+/* FGP_OPT_TCGEN05 (default 1): trailing updates behind a panel with at least 1024 rows left run on the 5th-generation
  * tensor cores (tcgen05.mma kind::i8 on exact base-128 digit slices of the panel, int32 accumulators in TMEM; csrc/ozaki.cuh);
  * 0 = the f64 DMMA kernel everywhere (A/B runs; both meet the 1e-10 factor tolerance). */
 enum fgp_option { FGP_OPT_LOOKAHEAD = 1, FGP_OPT_HEAD = 2, FGP_OPT_TCGEN05 = 3 };

@@ -135,7 +135,7 @@ def test_tcgen05_update_propagates_non_finite_rows():
 
 
 def test_fit_with_and_without_tcgen05_agree_and_meet_the_factor_tolerance():
-    """n = 4096: the first three panels' trailing updates run on tcgen05 (>= 2048 rows left), A/B against the f64 DMMA kernel
+    """n = 4096: the first six panels' trailing updates run on tcgen05 (>= 1024 rows left), A/B against the f64 DMMA kernel
     everywhere (FGP_OPT_TCGEN05 = 0); both within the 1e-10 factor tolerance of each other by a wide margin, same predictions."""
     F, N, O, make_dataset, make_inputs = _mods()
     n, d = 4096, 8

@@ -53,7 +53,7 @@ def test_single_rank_sharded_fit_matches_oracle_and_plain_fit(n, d):
 
 
 def test_single_rank_sharded_fit_on_the_tcgen05_path_is_bitwise_equal_and_predicts_alike():
-    """n = 4608: the first five panels have >= 2048 rows below them, so the sharded schedule's look-ahead update of the next
+    """n = 4608: the first seven panels have >= 1024 rows below them, so the sharded schedule's look-ahead update of the next
     panel's column block and its grouped trailing update run on tcgen05 (csrc/ozaki.cu) — same per-tile arithmetic as the
     single-GPU schedule, hence the same bits; the sharded fit also keeps the digit slices and every W_p, so predict takes the
     tcgen05 panel solve afterwards and must reproduce the plain model's predictions bit for bit."""

@@ -1,7 +1,7 @@
 """Small end-to-end run for compute-sanitizer (memcheck / racecheck / synccheck): the head kernel alone on 1..4 tiles, a fit
 through the head schedule (two panels + a partial one), predict (batched and latency paths), add_samples, LML gradient; the
 tcgen05 update kernel and its digit slicing alone (single-CTA and CTA-pair kernels) and inside a fit + predict + LML gradient
-large enough to route through them (n = 2560: 2048 rows below the first panel)."""
+large enough to route through them (n = 2560: 2048 rows below the first panel, threshold 1024)."""
 import ctypes as C
 import sys
 
