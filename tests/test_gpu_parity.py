@@ -399,6 +399,26 @@ def test_cholesky_failure_and_epsilon_semantics():
         F.GaussianProcess(F.ZeroPrior(), F.SquaredExp(1.0, 1.0), -0.1, None, X, y)  # mod.rs:150
 
 
+def test_cholesky_failure_behind_tcgen05_updates_reports_the_duplicate_column():
+    """The same semantics when the singular pivot sits behind several panels whose trailing updates ran on tcgen05 (n = 3200:
+    the duplicated point is row 3100; rows 0..3099 are distinct, so with zero noise the first exactly-singular pivot is column
+    3100), and cholesky_epsilon carries the factorisation through it."""
+    F, N, O, make_dataset, make_inputs = _mods()
+    n, d = 3200, 5
+    X, y = make_dataset(0x5EED0060, n, d)
+    X[3100] = X[7]
+    y[3100] = y[7]
+    with pytest.raises(ArithmeticError):
+        F.GaussianProcess(F.ZeroPrior(), F.SquaredExp(0.3, 1.0), 0.0, None, X, y)
+    h = N.Handle(0)
+    kd = F.SquaredExp(0.3, 1.0).device_desc()
+    rc = N.lib().fgp_fit(h.ptr, N.dptr(N.fcol(X)), n, n, d, N.dptr(y), C.byref(kd), 0.0, 0, 0.0)
+    assert rc == N.FGP_ERR_NOT_POSDEF and N.lib().fgp_failed_column(h.ptr) == 3100
+    h.close()
+    gp = F.GaussianProcess(F.ZeroPrior(), F.SquaredExp(0.3, 1.0), 0.0, 1e-6, X, y)
+    assert np.all(np.isfinite(np.tril(gp.cholesky_factor())))
+
+
 def test_bad_arguments_return_status_codes():
     F, N, O, make_dataset, make_inputs = _mods()
     h = N.Handle(0)
