@@ -206,10 +206,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "gp_fit_tflops", "value": val, "unit": "TFLOP/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak" if args.workload == "metric" else "strong",
-        "vs_baseline": None, "dtype": "f64",
-        "dtype_detail": "inputs, outputs and storage f64; O(n^3) trailing updates / solve updates computed as exact int8 x int8 -> int32 "
-                        "digit-slice products on tcgen05 (36 per f64 product, two f64 roundings per element and launch), panel chain "
-                        "in f64 on the DMMA pipe; same tolerances as a pure f64 path (tests/test_gpu_parity.py)", "data": "synthetic", "config": config,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
         "sample": {"n": ns, "q": qs, "d": d, "what": sample},
         "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": 1, "kind": "port", "sample": sample,
                          "fit_seconds_by_n": rows, "fitted_exponent": p,
@@ -233,9 +230,7 @@ def workload_config(workload, world, use_sharded, lookahead=True):
     return n, d, q, {"workload": desc, "n": n, "d": d, "q": q, "noise": 0.1, "kernel": "SquaredExp(ls=sqrt(d/6), ampl=1)",
                      "l2": "inputs larger than L2 (factor = %.2f GB)" % (8.0 * n * n / 1e9),
                      "multi_gpu": ("block-cyclic 512-column panels, NCCL panel broadcast, replicated factor; queries sharded")
-                     if use_sharded else "single GPU", "lookahead": lookahead,
-                     "trailing_updates": "tcgen05.mma kind::i8 on exact base-128 digit slices (8 slices, 36 products, int32 TMEM "
-                                         "accumulators) while >= 1024 rows are left, f64 DMMA below; results are f64"}
+                     if use_sharded else "single GPU", "lookahead": lookahead}
 
 
 def weak_n(world):
@@ -309,9 +304,11 @@ def run_ours(args, rank, local_rank, world):
         return float(t.item())
 
     lib.fgp_set_profiling(h.ptr, 0)
+    trailing = ("tcgen05.mma kind::i8 on exact base-128 digit slices (8 slices, 36 products, int32 TMEM accumulators) while >= 1024 "
+                "rows are left below the panel, f64 DMMA below that; results are f64")
     if args.no_tcgen05:
         lib.fgp_set_option(h.ptr, N.FGP_OPT_TCGEN05, 0)
-        config["trailing_updates"] = "f64 DMMA kernel everywhere (--no-tcgen05)"
+        trailing = "f64 DMMA kernel everywhere (--no-tcgen05)"
     if args.no_lookahead:
         lib.fgp_set_option(h.ptr, N.FGP_OPT_LOOKAHEAD, 0)
     fit_host()  # first touch: allocations, H2D
@@ -540,6 +537,7 @@ def run_ours(args, rank, local_rank, world):
         # whose N = 1 point is the metric's own configuration; the strong-scaling experiment of the north star (C4) is the
         # `strong_c4` block of every N > 1 line
         "scaling": "weak" if args.workload == "metric" else "strong", "vs_baseline": None, "dtype": "f64",
+        "trailing_updates": trailing,
         "dtype_detail": "inputs, outputs and storage f64; O(n^3) trailing updates / solve updates computed as exact int8 x int8 -> int32 "
                         "digit-slice products on tcgen05 (36 per f64 product, two f64 roundings per element and launch), panel chain "
                         "in f64 on the DMMA pipe; same tolerances as a pure f64 path (tests/test_gpu_parity.py)",
