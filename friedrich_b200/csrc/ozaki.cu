@@ -132,6 +132,7 @@ __device__ __forceinline__ uint64_t oz_desc(uint32_t saddr, uint32_t lbo, uint32
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, int (&v)[4]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
 }
+__device__ __forceinline__ void tma_wait_group_read1() { asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_group_all0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
@@ -311,26 +312,28 @@ ozaki_update_kernel(const __grid_constant__ GemmArgs g, const __grid_constant__ 
                     if (sum == 12345.678) g.C[0] = sum;   // keep phase 1 observable
                     continue;
                 }
-                // phase 2: x * (row scale * column scale) leaves through the warp's own 32 x 16 staging image, 16 columns at a time,
-                // as TMA reduce-adds into C (f64 add at the L2; the SM never reads C).  The two passes' additions to an element
-                // are applied in a fixed order: pass 0's reduces have been PERFORMED before pass 1 issues its first.
+                // phase 2: x * (row scale * column scale) leaves through the warp's own staging (two 32 x 8 images used in turn, so
+                // that one reduce can be in flight while the next image is written), 8 columns at a time, as TMA reduce-adds into C
+                // (f64 add at the L2; the SM never reads C).  The two passes' additions to an element are applied in a fixed order:
+                // pass 0's reduces have been PERFORMED before pass 1 issues its first.
                 if (lane == 0) {
                     if (pass == 1) tma_wait_group_all0();
                 }
 #pragma unroll
-                for (int cb = 0; cb < 4; ++cb) {
-                    const int c0 = half * 64 + cb * 16;
-                    if (lane == 0) tma_wait_group_read0();   // the previous image has been read
+                for (int cb = 0; cb < 8; ++cb) {
+                    const int c0 = half * 64 + cb * 8;
+                    double* img = stg + (cb & 1) * (32 * 8);
+                    if (lane == 0) tma_wait_group_read1();   // the image written two rounds ago has been read
                     __syncwarp();
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        const double val = x[cb * 16 + c] * (rf * __ldg(o.scB + n0 + c0 + c));
-                        stg[c * 32 + lane] = (diag && row < c0 + c) ? 0.0 : val;
+                    for (int c = 0; c < 8; ++c) {
+                        const double val = x[cb * 8 + c] * (rf * __ldg(o.scB + n0 + c0 + c));
+                        img[c * 32 + lane] = (diag && row < c0 + c) ? 0.0 : val;
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_reduce_add_2d(&tmC, m0 + quarter * 32, n0 + c0, stg);
+                        tma_reduce_add_2d(&tmC, m0 + quarter * 32, n0 + c0, img);
                         tma_commit_group();
                     }
                 }
@@ -742,7 +745,8 @@ int64_t ozaki_update_launch(const GemmArgs& g, const int8_t* digitsA, const doub
     gemm_nt_plan(p);
     alignas(64) CUtensorMap tmC;
     const int64_t ncols = g.lower ? g.M : g.N;
-    if (!make_tile_map(&tmC, g.C, g.M, ncols, g.ldc, 32, 16)) {
+    // box of the epilogue's reduce-adds: 32 rows x 8 columns (single-CTA kernel) / 32 x 16 (CTA-pair experiment)
+    if (!make_tile_map(&tmC, g.C, g.M, ncols, g.ldc, 32, (g_oz_exp & 32) ? 16 : 8)) {
         gemm_nt_flag_error();
         return 0;
     }
