@@ -17,6 +17,9 @@
 #include "ozaki.cuh"
 #include "sharded.cuh"
 
+#include <cstdlib>
+#include <vector>
+
 #include <algorithm>
 #include <functional>
 #include <string>
@@ -255,6 +258,21 @@ int factor_sharded_head(fgp_model* m, const fgp_kernel_desc* kd, const KernelTra
         cnt.launches += gemm_nt_launch(g, c) > 0;
     };
     bool copy_pending[2] = {false, false};
+    // tiles per CTA of the main-stream updates when several GPUs take turns as panel owners: short-lived CTAs (one tile, 34 us) hand
+    // SMs to the owner's high-priority chain kernels (head, panel solve) sooner than the wave-filling default (up to 4 tiles)
+    static const int OZ_SHARDED_TPC = getenv("FGP_SHARD_TPC") ? atoi(getenv("FGP_SHARD_TPC")) : 1;
+    // FGP_SHARD_TRACE=1: per-panel timeline of this rank (ms since the first record), printed by every rank at the end of the fit
+    static const bool trace = getenv("FGP_SHARD_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](int64_t pnl, int what, cudaStream_t stm) {
+        if (!trace) return;
+        if (tev.empty()) {
+            tev.resize((size_t)NP * 6 + 1);
+            for (auto& e : tev) cudaEventCreate(&e);
+            cudaEventRecord(tev.back(), m->st);
+        }
+        cudaEventRecord(tev[(size_t)pnl * 6 + what], stm);
+    };
     // digit slices of panel q: kept per panel when the model holds a store for them (prepare_head_work), else one scratch image
     auto oz_dig = [&](int64_t q) { return w.oz_digits + ((w.oz_off_bytes && w.oz_off_bytes[q] >= 0) ? w.oz_off_bytes[q] : 0); };
     auto oz_sc = [&](int64_t q) { return w.oz_scale + ((w.oz_off_rows && w.oz_off_rows[q] >= 0) ? w.oz_off_rows[q] : 0); };
@@ -299,15 +317,18 @@ int factor_sharded_head(fgp_model* m, const fgp_kernel_desc* kd, const KernelTra
                     CU(m, cudaEventRecord(m->evC, m->st3));
                 }
             }
+            mark(p, 0, m->st2);
             launch_potrf_head(Ajj, m->cap, (int)(Jend - J), w.inv + J * TILE * TILE, w.W + p * HEAD_PANEL * HEAD_PANEL, w.P,
                               w.sync + p * HEAD_SYNC_INTS, has_eps, eps, m->info_d, (int)(J * TILE), pc);
             cnt.launches += 1;
+            mark(p, 1, m->st2);
             CU(m, cudaMemcpy2DAsync(buf, rows * sizeof(double), Ajj, m->cap * sizeof(double), wc * sizeof(double), (size_t)wc,
                                     cudaMemcpyDeviceToDevice, m->st2));
             if (below > 0) {
                 if (p >= 1) CU(m, cudaStreamWaitEvent(m->st2, m->evC, 0));
                 gemm(buf + wc, rows, A21, m->cap, w.W + p * HEAD_PANEL * HEAD_PANEL, HEAD_PANEL, below, wc, wc, 1.0, 0, 0, 1, pc);
             }
+            mark(p, 2, m->st2);
             CU(m, cudaEventRecord(cm->ev_col, m->st2));
             CU(m, cudaStreamWaitEvent(cm->st_comm, cm->ev_col, 0));
             if (below > 0) {  // L21 <- buffer, off the critical path (nothing reads these columns of L before the fit ends)
@@ -333,16 +354,28 @@ int factor_sharded_head(fgp_model* m, const fgp_kernel_desc* kd, const KernelTra
             NC(m, nccl->Broadcast(Wp, Wp, (size_t)HEAD_PANEL * HEAD_PANEL, ncclDouble, owner, cm->comm, cm->st_comm));
             cm->bcast_bytes += (double)HEAD_PANEL * HEAD_PANEL * sizeof(double);
         }
+        mark(p, 3, cm->st_comm);
         CU(m, cudaEventRecord(cm->ev_bcast, cm->st_comm));
         CU(m, cudaStreamWaitEvent(m->st2, cm->ev_bcast, 0));  // the next owner's look-ahead reads the buffer on st2 / st3
         CU(m, cudaStreamWaitEvent(m->st, cm->ev_bcast, 0));
+        mark(p, 4, m->st);
         // tcgen05 updates (csrc/ozaki.cuh) while >= OZ_MIN_ROWS rows are left below the panel: every rank slices the rows below the
         // diagonal block into base-128 digits (tile 0 of the digit buffer = first row below the panel)
         const bool oz = w.oz_digits && below >= OZ_MIN_ROWS;
         if (oz) {
-            ozaki_slice_launch(buf + wc, rows, below, (int)wc, oz_dig(p), oz_sc(p), mc);
+            if (w.oz_off_bytes) {
+                // every panel has its own digit image, so the slicing does not have to queue behind the main stream's update with
+                // the PREVIOUS panel: it runs on the side stream as soon as the panel has arrived — the next owner's look-ahead
+                // (which reads these digits) then waits for the transfer only, not for this rank's trailing update
+                CU(m, cudaStreamWaitEvent(m->st3, cm->ev_bcast, 0));
+                ozaki_slice_launch(buf + wc, rows, below, (int)wc, oz_dig(p), oz_sc(p), sc);
+                CU(m, cudaEventRecord(m->evD, m->st3));
+                CU(m, cudaStreamWaitEvent(m->st, m->evD, 0));
+            } else {
+                ozaki_slice_launch(buf + wc, rows, below, (int)wc, oz_dig(p), oz_sc(p), mc);
+                CU(m, cudaEventRecord(m->evD, m->st));
+            }
             cnt.launches += 2;
-            CU(m, cudaEventRecord(m->evD, m->st));
         }
         {
             // every owned panel c > p, c != p+1, in ONE launch: the owned panels are groups of PT tile columns, P*PT apart
@@ -362,7 +395,7 @@ int factor_sharded_head(fgp_model* m, const fgp_kernel_desc* kd, const KernelTra
                 if (oz) {
                     const int64_t toff = c0 - Jend;   // C's origin in tiles below the panel
                     const int8_t* dg = oz_dig(p) + toff * (wc / OZ_KSTEP) * (int64_t)OZ_PART_BYTES;
-                    cnt.launches += ozaki_update_launch(g, dg, oz_sc(p) + toff * TILE, dg, oz_sc(p) + toff * TILE, 0, mc) > 0;
+                    cnt.launches += ozaki_update_launch(g, dg, oz_sc(p) + toff * TILE, dg, oz_sc(p) + toff * TILE, P > 1 ? OZ_SHARDED_TPC : 0, mc) > 0;
                 } else {
                     cnt.launches += gemm_nt_launch(g, mc) > 0;
                 }
@@ -372,6 +405,22 @@ int factor_sharded_head(fgp_model* m, const fgp_kernel_desc* kd, const KernelTra
             CU(m, cudaMemcpy2DAsync(m->L.p + J * TILE + J * TILE * m->cap, m->cap * sizeof(double), buf, rows * sizeof(double),
                                     rows * sizeof(double), (size_t)wc, cudaMemcpyDeviceToDevice, m->st));
         CU(m, cudaEventRecord(cm->ev_trail[p & 1], m->st));
+        mark(p, 5, m->st);
+    }
+    if (trace && !tev.empty()) {
+        cudaStreamSynchronize(m->st);
+        cudaStreamSynchronize(m->st2);
+        cudaStreamSynchronize(cm->st_comm);
+        fprintf(stderr, "[shard trace rank %d] panel owner | lookahead-done(head start) head-done solve-done | bcast-done | main-start main-end (ms)\n", r);
+        for (int64_t pnl = 0; pnl < NP; ++pnl) {
+            float t[6] = {-1, -1, -1, -1, -1, -1};
+            for (int k = 0; k < 6; ++k)
+                if (cudaEventQuery(tev[(size_t)pnl * 6 + k]) == cudaSuccess) cudaEventElapsedTime(&t[k], tev.back(), tev[(size_t)pnl * 6 + k]);
+            cudaGetLastError();
+            fprintf(stderr, "[shard trace rank %d] %3lld %d | %8.3f %8.3f %8.3f | %8.3f | %8.3f %8.3f\n", r, (long long)pnl, shard_owner(pnl, P), t[0], t[1], t[2],
+                    t[3], t[4], t[5]);
+        }
+        for (auto& e : tev) cudaEventDestroy(e);
     }
     // join the panel and side streams; the inverted diagonal tiles live with their owners and every rank needs them for the solves
     CU(m, cudaEventRecord(cm->ev_col, m->st2));
