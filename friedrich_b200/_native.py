@@ -106,6 +106,7 @@ SIGNATURES = {
                                         _i64]),
     "fgp_dbg_potrf_head": (C.c_int, [C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_double, C.POINTER(C.c_int), C.c_int, _dp]),
     "fgp_dbg_exp": (C.c_double, [C.c_double]),
+    "fgp_dbg_exp_tab": (C.c_double, [C.c_double]),
     "fgp_dbg_gemm_occupancy": (C.c_int, [C.c_int]),
     "fgp_dbg_gemm_occupancy32": (C.c_int, [C.c_int]),
     "fgp_dbg_gemm_cta_rows": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -1358,6 +1358,11 @@ FGP_EXPORT int fgp_dbg_potrf_head(int device, double* A, int nt, double* W, int 
 // =================================================================================================================
 // test hook: the production GEMM on host matrices
 FGP_EXPORT double fgp_dbg_exp(double x) { return exp_nonpos(x); }
+// host twin of the table-assisted exp of the pair-tile fast path (unit scale)
+FGP_EXPORT double fgp_dbg_exp_tab(double x) {
+    static const double tab[256] = {FGP_EXP2_TABLE_256};
+    return exp_nonpos_tab(x, tab);
+}
 
 FGP_EXPORT int fgp_dbg_gemm_occupancy(int device) {
     DeviceGuard dg(device);

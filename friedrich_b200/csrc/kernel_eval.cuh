@@ -9,6 +9,7 @@
 
 #include "../../include/fgp_kernel_desc.h"
 #include "common.cuh"
+#include "exp_table.cuh"
 
 namespace fgp {
 
@@ -69,6 +70,53 @@ __host__ __device__ __forceinline__ double exp_nonpos(double x) {
     memcpy(&v, &bits, 8);
 #endif
     return (x < -708.0) ? 0.0 : v;
+}
+
+// Table-assisted exp for the interior-tile fast path of pair_tile_kernel, where the fp64 pipe is the limit (the 13-term
+// polynomial above is half of a pair's fp64 instructions): x = (256 e + j) ln2/256 + r with |r| <= ln2/512, so
+// exp(x) = T + T p(r), T = 2^e 2^(j/256), p = exp(r) - 1 by a degree-4 Taylor polynomial (truncation 3.8e-17) and a 256-entry
+// table (tools/gen_exp_table.py, correctly rounded).  `tab` holds s * 2^(j/256) for a caller-chosen scale s (the kernel
+// amplitude, folded in when the CTA copies the table into shared memory; 2^-150 <= s <= 2^150 so that the exponent
+// insertion stays inside the normal range): returns s * exp(x), <= 1.5 ulp of exp on [-600, 0] (tests/test_abi.py through
+// fgp_dbg_exp_tab).  The clamp and the exponent insertion are integer instructions; 9 fp64 instructions in all.
+// x <= -600 gives 0 (true value < 1e-260), NaN stays NaN.
+__host__ __device__ __forceinline__ void dbl_split(double v, int& hi, int& lo) {
+#ifdef __CUDA_ARCH__
+    hi = __double2hiint(v);
+    lo = __double2loint(v);
+#else
+    long long b;
+    memcpy(&b, &v, 8);
+    hi = (int)(b >> 32);
+    lo = (int)(b & 0xffffffffll);
+#endif
+}
+__host__ __device__ __forceinline__ double dbl_join(int hi, int lo) {
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(hi, lo);
+#else
+    const long long b = ((long long)hi << 32) | (long long)(unsigned)lo;
+    double v;
+    memcpy(&v, &b, 8);
+    return v;
+#endif
+}
+__host__ __device__ __forceinline__ double exp_nonpos_tab(double x, const double* tab) {
+    const double t = fma(x, 369.3299304675746, 6755399441055744.0);   // 256/ln2; the low word of t holds n = 256 e + j
+    const double n = t - 6755399441055744.0;
+    double r = fma(n, -6.93147180369123816490e-01 * 0.00390625, x);   // ln2_hi / 256: 32 significant bits, n * it is exact
+    r = fma(n, -1.90821492927058770002e-10 * 0.00390625, r);
+    const double r2 = r * r;
+    double q = fma(4.1666666666666664e-02, r, 1.6666666666666666e-01);
+    q = fma(q, r, 0.5);
+    const double p = fma(q, r2, r);                                   // exp(r) - 1
+    int thi, ni, Thi, Tlo, xhi, xlo;
+    dbl_split(t, thi, ni);
+    dbl_split(x, xhi, xlo);
+    dbl_split(tab[ni & 255], Thi, Tlo);
+    const double T = dbl_join(Thi + (int)((unsigned)(ni >> 8) << 20), Tlo);   // * 2^e, e >= -866
+    const double v = fma(T, p, T);
+    return ((unsigned)xhi >= 0xC082C000u) ? 0.0 : v;                  // x <= -600 (negative doubles order like their bits)
 }
 
 __device__ __forceinline__ double dsignum(double v) { return (v != v) ? v : (signbit(v) ? -1.0 : 1.0); }

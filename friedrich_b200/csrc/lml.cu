@@ -19,7 +19,8 @@ struct LmlEpi {
     __device__ __forceinline__ bool fast_ok(int64_t, int64_t, int) const { return false; }
     __device__ __forceinline__ double* fast_base(int64_t, int64_t) const { return nullptr; }
     __device__ __forceinline__ int fast_ld() const { return 0; }
-    __device__ __forceinline__ double fast_value(double) const { return 0.0; }
+    __device__ __forceinline__ double fast_scale() const { return 1.0; }
+    __device__ __forceinline__ double fast_value(double, const double*) const { return 0.0; }
     DevKernel k;
     const double* kinv;
     int64_t ld;
@@ -65,7 +66,8 @@ struct DistEpi {
     __device__ __forceinline__ bool fast_ok(int64_t, int64_t, int) const { return false; }
     __device__ __forceinline__ double* fast_base(int64_t, int64_t) const { return nullptr; }
     __device__ __forceinline__ int fast_ld() const { return 0; }
-    __device__ __forceinline__ double fast_value(double) const { return 0.0; }
+    __device__ __forceinline__ double fast_scale() const { return 1.0; }
+    __device__ __forceinline__ double fast_value(double, const double*) const { return 0.0; }
     int64_t n;
     double* partial;
     double acc[1];

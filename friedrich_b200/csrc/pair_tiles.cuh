@@ -35,6 +35,9 @@ struct PairArgs {
     int symmetric;       // rows and columns are the same point set: only r >= c is visited
 };
 
+// 2^(j/256) for exp_nonpos_tab (every translation unit that instantiates pair_tile_kernel keeps its own copy: no -rdc)
+static __device__ const double g_exp2_tab[256] = {FGP_EXP2_TABLE_256};
+
 constexpr int PAIR_TM = 128;  // tile rows
 constexpr int PAIR_TN = 64;   // tile columns
 
@@ -46,6 +49,13 @@ template <int MODE, class Epi>
 __global__ void __launch_bounds__(256) pair_tile_kernel(PairArgs a, const __grid_constant__ Epi epi_in) {
     Epi epi = epi_in;   // accumulating epilogues keep per-thread state
     epi.bind(&epi_in);  // ... while a TMA descriptor must be addressed in the kernel-parameter space
+    // exp table of the interior-tile fast path, scaled by the epilogue's amplitude (exp_nonpos_tab, kernel_eval.cuh)
+    constexpr bool FAST = (MODE == PAIR_D2) && Epi::HAS_FAST;
+    __shared__ double exp_tab[FAST ? 256 : 1];
+    if (FAST) {
+        exp_tab[threadIdx.x] = epi.fast_scale() * __ldg(&g_exp2_tab[threadIdx.x]);
+        __syncthreads();
+    }
     const int64_t row0 = (int64_t)(blockIdx.x + a.row_tile0) * PAIR_TM;
     const int64_t col0 = (int64_t)(blockIdx.y + a.col_tile0) * PAIR_TN;
     const bool active = !(a.symmetric && row0 + PAIR_TM - 1 < col0);
@@ -107,7 +117,9 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(PairArgs a, const __grid
         // per-pair guards (r == c, r < c, r / c beyond the valid extent) and the 64-bit index arithmetic of the general
         // path below are most of its instructions — here every pair is d2, the repair test, the kernel value and one store
         // at a 32-bit offset from a per-thread base.  (block-uniform branch)
-        if (MODE == PAIR_D2 && Epi::HAS_FAST && epi.fast_ok(row0, col0, a.symmetric)) {
+        if (FAST && epi.fast_ok(row0, col0, a.symmetric)) {
+            // the clamp at 0 and the repair test work on the high words (integer pipe; the fp64 pipe is this path's limit):
+            // d2 < 0 <=> sign bit, d2 < nsum 2^-12 <=> exponent/mantissa-high comparison (both operands >= 0 there)
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
@@ -116,9 +128,10 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(PairArgs a, const __grid
 #pragma unroll
                     for (int mi = 0; mi < 4; ++mi) {
                         const double nsum = nrow[mi] + ncol;
-                        const double d2 = fmax(fma(-2.0, acc[mi][ni][e], nsum), 0.0);
-                        if (d2 < nsum * 0x1p-12) fix |= 1u << ((ni * 2 + e) * 4 + mi);
-                        d2v[mi][ni][e] = d2;
+                        const double d2 = fma(-2.0, acc[mi][ni][e], nsum);
+                        const int hd = __double2hiint(d2);
+                        if (hd < __double2hiint(nsum) - (12 << 20)) fix |= 1u << ((ni * 2 + e) * 4 + mi);
+                        d2v[mi][ni][e] = __hiloint2double(hd < 0 ? 0 : hd, hd < 0 ? 0 : __double2loint(d2));
                     }
                 }
             if (fix) {
@@ -146,7 +159,7 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(PairArgs a, const __grid
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
 #pragma unroll
-                    for (int mi = 0; mi < 4; ++mi) obase[8 * mi + (8 * ni + e) * ldi] = epi.fast_value(d2v[mi][ni][e]);
+                    for (int mi = 0; mi < 4; ++mi) obase[8 * mi + (8 * ni + e) * ldi] = epi.fast_value(d2v[mi][ni][e], exp_tab);
             epi.finish(row0, col0, active);
             return;
         }
@@ -255,14 +268,16 @@ struct CovWriteEpi {
     static constexpr bool HAS_FAST = (KIND == KIND_SQEXP || KIND == KIND_MATERN2);
     __device__ __forceinline__ bool fast_ok(int64_t row0, int64_t col0, int sym) const {
         return ld < (int64_t)1 << 24 && row0 + PAIR_TM <= valid_rows && col0 + PAIR_TN <= valid_cols &&
-               (!sym || row0 >= col0 + PAIR_TN);
+               (!sym || row0 >= col0 + PAIR_TN) && c1 >= 0x1p-150 && c1 <= 0x1p150;  // amplitude range of exp_nonpos_tab
     }
     __device__ __forceinline__ double* fast_base(int64_t r, int64_t c) const { return out + r + c * ld; }
     __device__ __forceinline__ int fast_ld() const { return (int)ld; }
-    __device__ __forceinline__ double fast_value(double d2) const {
-        if (KIND == KIND_SQEXP) return c1 * exp_nonpos(d2 * c0);
+    __device__ __forceinline__ double fast_scale() const { return c1; }
+    // tab = c1 * 2^(j/256): exp_nonpos_tab returns c1 * exp(.)
+    __device__ __forceinline__ double fast_value(double d2, const double* tab) const {
+        if (KIND == KIND_SQEXP) return exp_nonpos_tab(d2 * c0, tab);
         const double x = c0 * sqrt(d2);
-        return c1 * (1.0 + x + c2 * d2) * exp_nonpos(-x);
+        return (1.0 + x + c2 * d2) * exp_nonpos_tab(-x, tab);
     }
     __device__ __forceinline__ void operator()(int64_t r, int64_t c, double dot, double d2) const {
         double v;

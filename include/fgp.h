@@ -211,6 +211,9 @@ int fgp_dbg_potrf_head(int device, double* A, int nt, double* W, int has_sub, do
 
 /* test hook, host only: the branch-free exp(x), x <= 0, that the device kernels evaluate (csrc/kernel_eval.cuh exp_nonpos) */
 double fgp_dbg_exp(double x);
+/* test hook, host only: the table-assisted exp(x), x <= 0, of the Gram / cross-covariance interior tiles (exp_nonpos_tab:
+ * 256-entry 2^(j/256) table + degree-4 polynomial; 0 for x <= -600) */
+double fgp_dbg_exp_tab(double x);
 
 /* test hook: resident CTAs per SM of the GEMM kernel on `device` (the design point is 2: one CTA's C read-modify-write
  * overlaps the other's DMMA main loop); -1 on error */

@@ -91,6 +91,29 @@ def test_branch_free_exp_is_accurate_to_two_ulp():
     assert math.isnan(lib.fgp_dbg_exp(float("nan")))
 
 
+def test_table_assisted_exp_is_accurate_to_two_ulp():
+    """csrc/kernel_eval.cuh exp_nonpos_tab (host twin through fgp_dbg_exp_tab): the exp of the Gram / cross-covariance
+    interior tiles (2^(j/256) table + degree-4 polynomial, integer-side clamp)."""
+    import math
+    import numpy as np
+    from friedrich_b200 import _native as N
+    lib = N.lib()
+    rng = np.random.default_rng(11)
+    ln2_256 = math.log(2.0) / 256.0
+    xs = np.concatenate([-rng.random(30000) * 50.0, -rng.random(8000) * 599.0, -np.logspace(-300, 0, 2000),
+                         # reduction boundaries: x near (k + 1/2) ln2/256, where |r| is largest
+                         -(rng.integers(0, 150000, 4000) + 0.5) * ln2_256 * (1.0 + 1e-15 * rng.standard_normal(4000)),
+                         [0.0, -0.0, -0.5 * math.log(2.0), -math.log(2.0), -599.999, -1e-320]])
+    worst = 0.0
+    for x in xs:
+        got, ref = lib.fgp_dbg_exp_tab(float(x)), math.exp(float(x))
+        worst = max(worst, abs(got - ref) / np.spacing(ref))
+    assert worst <= 1.5, worst
+    assert lib.fgp_dbg_exp_tab(-600.0) == 0.0 and lib.fgp_dbg_exp_tab(-1e9) == 0.0
+    assert lib.fgp_dbg_exp_tab(-float("inf")) == 0.0
+    assert math.isnan(lib.fgp_dbg_exp_tab(float("nan")))
+
+
 def test_gemm_cta_shape_rule():
     """Host rule of csrc/gemm_nt.cu: 32-row CTAs exactly where they lower the heaviest SM's load on a 148-SM part —
     i = 2 * tiles 64-row items: i <= 74 (0.5 vs 1 unit per SM) or 148 < i <= 222 (1.5 vs 2)."""
