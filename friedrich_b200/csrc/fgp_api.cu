@@ -399,11 +399,17 @@ void comm_release(fgp_model* m) {
         cudaStreamSynchronize(c->st_comm);
         cudaStreamDestroy(c->st_comm);
     }
+    if (c->st_copy) {
+        cudaStreamSynchronize(c->st_copy);
+        cudaStreamDestroy(c->st_copy);
+    }
     if (c->ev_col) cudaEventDestroy(c->ev_col);
     if (c->ev_bcast) cudaEventDestroy(c->ev_bcast);
     for (cudaEvent_t e : c->ev_trail)
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_copy)
+        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_pipe)
         if (e) cudaEventDestroy(e);
     delete c;
     m->comm = nullptr;
@@ -1104,6 +1110,7 @@ FGP_EXPORT int fgp_comm_init_rank(fgp_model* m, const void* id, size_t bytes, in
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithPriority(&c->st_comm, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&c->st_copy, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_col, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_bcast, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_trail[0], cudaEventDisableTiming) != cudaSuccess ||
@@ -1178,7 +1185,8 @@ int run_factor_sharded(fgp_model* m, const fgp_kernel_desc* kernel, const Kernel
     int64_t p0 = 0;
     FGP_TRY(prepare_head_work(m, 0, &w, &p0));
     m->w_valid = false;
-    const int rc = factor_sharded_head(m, kernel, kt, noise, has_eps, eps, w);
+    static const bool pipe = !(getenv("FGP_SHARD_PIPE") && atoi(getenv("FGP_SHARD_PIPE")) == 0);
+    const int rc = pipe ? factor_sharded_pipe(m, kernel, kt, noise, has_eps, eps, w) : factor_sharded_head(m, kernel, kt, noise, has_eps, eps, w);
     if (rc == FGP_OK) {
         // every rank ends with the full factor, every panel's inverse diagonal block W_p (broadcast beside the panel) and the digit
         // slices of every panel: predict / likelihood / LML gradient run locally like after a single-GPU fit

@@ -3,6 +3,8 @@
 // no counterpart (single-threaded crate); the entry points are declared in include/fgp.h (fgp_comm_*, fgp_fit_sharded).
 #pragma once
 
+#include <vector>
+
 #include "nccl_dyn.cuh"
 
 #include "kernel_eval.cuh"
@@ -14,10 +16,12 @@ struct fgp_comm {
     int nranks = 1, rank = 0;
     fgp::DevBuf pbuf[2];                     // contiguous panel buffers: rows [J*128, np) x panel width, ld = rows
     cudaStream_t st_comm = nullptr;          // packs and broadcasts the panel slab by slab while the panel stream factors on
+    cudaStream_t st_copy = nullptr;          // factor_sharded_pipe: copies of the received panel pieces into L (high priority: a buffer is free again only after its copy, and a low-priority copy would queue behind every pending CTA of the trailing update)
     cudaEvent_t ev_col = nullptr;            // a block column of the panel is final (recorded on the panel stream)
     cudaEvent_t ev_bcast = nullptr;          // panel J has arrived (recorded on the comm stream)
     cudaEvent_t ev_trail[2] = {nullptr, nullptr};  // trailing update with panel J done (main stream), index J & 1
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};   // this rank's copy of panel buffer J & 1 back into L done (side stream)
+    std::vector<cudaEvent_t> ev_pipe;        // factor_sharded_pipe: [panel parity][solve | bcast | sliced | look-ahead][piece]
     double bcast_bytes = 0.0;                // bytes this rank sent or received in the last sharded factorisation
 };
 
@@ -33,6 +37,11 @@ int reserve_sharded(fgp_model* m);
 int factor_sharded(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& kt, double noise, int has_eps, double eps);
 // the same on the head schedule (one potrf_head_kernel per panel; bit-identical to the single-GPU head schedule)
 int factor_sharded_head(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& kt, double noise, int has_eps, double eps,
+                        const PotrfWork& w);
+
+// the head schedule with the panel travelling in row pieces: solve, broadcast, digit slicing and the next owner's look-ahead
+// overlap piece by piece, the next head starts after the first 4 MB (sharded.cu); same arithmetic, bit-identical factor
+int factor_sharded_pipe(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& kt, double noise, int has_eps, double eps,
                         const PotrfWork& w);
 
 }  // namespace fgp
