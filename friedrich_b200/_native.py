@@ -105,6 +105,7 @@ SIGNATURES = {
     "fgp_dbg_lower_tiles_skip": (_i64, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                         _i64]),
     "fgp_dbg_potrf_head": (C.c_int, [C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_double, C.POINTER(C.c_int), C.c_int, _dp]),
+    "fgp_dbg_shard_pieces": (C.c_int, [C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),
     "fgp_dbg_exp": (C.c_double, [C.c_double]),
     "fgp_dbg_exp_tab": (C.c_double, [C.c_double]),
     "fgp_dbg_gemm_occupancy": (C.c_int, [C.c_int]),

@@ -1365,6 +1365,18 @@ FGP_EXPORT int fgp_dbg_potrf_head(int device, double* A, int nt, double* W, int 
 
 // =================================================================================================================
 // test hook: the production GEMM on host matrices
+// test hook, host only: the row pieces of a panel with `below` rows under its diagonal block (sharded.cuh shard_pieces)
+FGP_EXPORT int fgp_dbg_shard_pieces(int64_t below, int64_t pipe_rows, int64_t* first_row, int64_t* height, int cap) {
+    if (below < 1024 || below % 128 != 0 || pipe_rows < 128 || !first_row || !height) return -1;
+    std::vector<std::pair<int64_t, int64_t>> rh;
+    shard_pieces(below, pipe_rows, rh);
+    if ((int)rh.size() > cap) return -1;
+    for (size_t i = 0; i < rh.size(); ++i) {
+        first_row[i] = rh[i].first;
+        height[i] = rh[i].second;
+    }
+    return (int)rh.size();
+}
 FGP_EXPORT double fgp_dbg_exp(double x) { return exp_nonpos(x); }
 // host twin of the table-assisted exp of the pair-tile fast path (unit scale)
 FGP_EXPORT double fgp_dbg_exp_tab(double x) {

@@ -527,18 +527,11 @@ int factor_sharded_pipe(fgp_model* m, const fgp_kernel_desc* kd, const KernelTra
             return q;
         }
         double* at = q.buf + q.wc * q.wc;
-        int64_t r0 = 0;
-        auto push = [&](int64_t h) {
-            q.pcs.push_back({r0, h, at, h});
-            at += h * q.wc;
-            r0 += h;
-        };
-        push(HEAD_PANEL);                                           // the next panel's diagonal-block rows
-        if (q.below - r0 > 0) push(std::min<int64_t>(HEAD_PANEL, q.below - r0));   // ... and the rows of the panel after it
-        const int64_t rest_tiles = (q.below - r0) / TILE;
-        if (rest_tiles > 0) {
-            const int64_t k = (rest_tiles * TILE + PIPE_ROWS - 1) / PIPE_ROWS;
-            for (int64_t i = 0; i < k; ++i) push((rest_tiles / k + (i < rest_tiles % k ? 1 : 0)) * TILE);
+        std::vector<std::pair<int64_t, int64_t>> rh;
+        shard_pieces(q.below, PIPE_ROWS, rh);
+        for (const auto& x : rh) {
+            q.pcs.push_back({x.first, x.second, at, x.second});
+            at += x.second * q.wc;
         }
         return q;
     };

@@ -3,6 +3,8 @@
 // no counterpart (single-threaded crate); the entry points are declared in include/fgp.h (fgp_comm_*, fgp_fit_sharded).
 #pragma once
 
+#include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "nccl_dyn.cuh"
@@ -29,6 +31,24 @@ namespace fgp {
 
 // panel p (PANEL_TILES block columns) is owned by rank p % nranks
 inline int shard_owner(int64_t panel, int nranks) { return (int)(panel % nranks); }
+
+// row pieces of the `below` rows under a panel's diagonal block in factor_sharded_pipe (multiples of 128 rows): the next panel's
+// diagonal-block rows (512), the rows of the panel after it (<= 512), then the rest in equal pieces of at most pipe_rows rows.
+// Appends (first row, height) pairs; below >= 1024.
+inline void shard_pieces(int64_t below, int64_t pipe_rows, std::vector<std::pair<int64_t, int64_t>>& out) {
+    int64_t r0 = 0;
+    auto push = [&](int64_t h) {
+        out.push_back({r0, h});
+        r0 += h;
+    };
+    push(512);
+    if (below - r0 > 0) push(std::min<int64_t>(512, below - r0));
+    const int64_t rest_tiles = (below - r0) / 128;
+    if (rest_tiles > 0) {
+        const int64_t k = (rest_tiles * 128 + pipe_rows - 1) / pipe_rows;
+        for (int64_t i = 0; i < k; ++i) push((rest_tiles / k + (i < rest_tiles % k ? 1 : 0)) * 128);
+    }
+}
 
 // panel buffers for the current problem size (rank-local allocation; entry points call it BEFORE the cross-rank status exchange)
 int reserve_sharded(fgp_model* m);

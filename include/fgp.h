@@ -209,6 +209,10 @@ int fgp_dbg_gemm_bench(int device, int M, int N, int K, int lower, int beta_one,
 int fgp_dbg_potrf_head(int device, double* A, int nt, double* W, int has_sub, double sub, int* info_out, int reps,
                        double* ms_out); /* reps > 0 and ms_out != NULL: also the kernel's CUDA-event time on fresh copies of A */
 
+/* test hook, host only: the row pieces in which a panel with `below` rows under its diagonal block travels in the sharded fit
+ * (csrc/sharded.cuh shard_pieces); returns their number (<= cap) or -1 */
+int fgp_dbg_shard_pieces(int64_t below, int64_t pipe_rows, int64_t* first_row, int64_t* height, int cap);
+
 /* test hook, host only: the branch-free exp(x), x <= 0, that the device kernels evaluate (csrc/kernel_eval.cuh exp_nonpos) */
 double fgp_dbg_exp(double x);
 /* test hook, host only: the table-assisted exp(x), x <= 0, of the Gram / cross-covariance interior tiles (exp_nonpos_tab:

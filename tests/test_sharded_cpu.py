@@ -114,3 +114,29 @@ def test_lower_mode_tile_map_with_skipped_top_rows(tm, tn, grp, stride, skip):
     assert tiles == len(expect)
     got = [(ti[b], tj[b]) for b in range(tiles)]
     assert sorted(got) == sorted(expect)
+
+
+@pytest.mark.parametrize("pipe_rows", [1024, 4096, 8192])
+def test_sharded_panel_row_pieces_partition_the_rows(pipe_rows):
+    """factor_sharded_pipe ships the rows below a panel's diagonal block in pieces (csrc/sharded.cuh shard_pieces): they must
+    partition [0, below) in whole 128-row tiles, start with the next panel's diagonal-block rows (512) and the 512 rows of the
+    panel after it, and never exceed pipe_rows (rounded up to a tile) — for every panel of every problem size."""
+    import ctypes as C
+    from friedrich_b200 import _native as N
+    cap = 512
+    r0, h = (C.c_int64 * cap)(), (C.c_int64 * cap)()
+    for below in list(range(1024, 40 * 1024 + 1, 128)) + [65536 - 512, 131072 - 512]:
+        k = N.lib().fgp_dbg_shard_pieces(below, pipe_rows, r0, h, cap)
+        assert k >= 2, (below, k)
+        pcs = [(r0[i], h[i]) for i in range(k)]
+        assert pcs[0] == (0, 512) and pcs[1] == (512, 512)
+        at = 0
+        for first, height in pcs:
+            assert first == at and height > 0 and height % 128 == 0
+            at += height
+        assert at == below
+        assert all(height <= pipe_rows + 127 for _, height in pcs[2:])
+        rest = [height for _, height in pcs[2:]]
+        assert not rest or max(rest) - min(rest) <= 128   # equal pieces up to one tile
+    assert N.lib().fgp_dbg_shard_pieces(512, pipe_rows, r0, h, cap) == -1      # one-piece panels are not cut
+    assert N.lib().fgp_dbg_shard_pieces(1024 + 64, pipe_rows, r0, h, cap) == -1
