@@ -49,3 +49,15 @@ if "--small" not in sys.argv:
     m3, v3 = gp2.predict_mean_variance(Xq)
     s2, g2 = gp2.scaled_gradient_marginal_likelihood()
     print("ok tcgen05 fit", float(m3[0]), float(v3[0]), s2, g2)
+    # single-rank sharded fit on the row-piece schedule (csrc/sharded.cu factor_sharded_pipe): n = 2560 -> panels 0..2 travel in
+    # pieces (512, 512, rest), the last two in one piece; then predict from the kept digit slices
+    from friedrich_b200 import sharded  # noqa: E402
+    from friedrich_b200.kernels import SquaredExp  # noqa: E402
+    hs = N.Handle(0)
+    sharded.comm_init(hs, 0, 1)
+    kd = SquaredExp(0.8, 1.0).device_desc()
+    sharded.fit_sharded(hs, X2, y2, kd, 0.1)
+    mean, var = np.zeros(200), np.zeros(200)
+    hs.check(N.lib().fgp_predict_mean_var(hs.ptr, C.byref(kd), N.dptr(N.fcol(Xq)), 200, 200, N.dptr(mean), N.dptr(var)))
+    print("ok sharded pipe fit", float(mean[0]), float(var[0]), "plain", float(m3[0]), float(v3[0]))
+    hs.close()
