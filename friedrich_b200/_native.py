@@ -20,6 +20,7 @@ MAX_PARAMS = 24
 FGP_OPT_LOOKAHEAD = 1
 FGP_OPT_HEAD = 2
 FGP_OPT_TCGEN05 = 3
+FGP_OPT_SHARD_PIPE = 4
 FGP_COMM_ID_BYTES = 128
 FGP_OK, FGP_ERR_NOT_POSDEF, FGP_ERR_BAD_ARG, FGP_ERR_BAD_KERNEL, FGP_ERR_CUDA, FGP_ERR_NOT_FITTED, FGP_ERR_COMM = range(7)
 

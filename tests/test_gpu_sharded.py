@@ -52,14 +52,15 @@ def test_single_rank_sharded_fit_matches_oracle_and_plain_fit(n, d):
     assert np.array_equal(np.tril(_factor(N, hs, n)), np.tril(_factor(N, hp, n)))
 
 
-@pytest.mark.parametrize("n", [4608, 10600])
-def test_single_rank_sharded_fit_on_the_tcgen05_path_is_bitwise_equal_and_predicts_alike(n):
+@pytest.mark.parametrize("n,pipe", [(4608, 1), (10600, 1), (4608, 0)])
+def test_single_rank_sharded_fit_on_the_tcgen05_path_is_bitwise_equal_and_predicts_alike(n, pipe):
     """n = 4608: the first seven panels have >= 1024 rows below them, so the sharded schedule's look-ahead update of the next
     panel's column block and its grouped trailing update run on tcgen05 (csrc/ozaki.cu) — same per-tile arithmetic as the
     single-GPU schedule, hence the same bits; the sharded fit also keeps the digit slices and every W_p, so predict takes the
     tcgen05 panel solve afterwards and must reproduce the plain model's predictions bit for bit.  n = 10600 (np = 10624: a
     narrower last panel) makes the early panels travel in FOUR row pieces (512, 512, 2 x <= 8192: csrc/sharded.cu
-    factor_sharded_pipe) and ends with one-piece panels: every transition of the row-piece schedule on one rank."""
+    factor_sharded_pipe) and ends with one-piece panels: every transition of the row-piece schedule on one rank.  pipe = 0:
+    the one-piece schedule (factor_sharded_head, FGP_OPT_SHARD_PIPE = 0) must give the same bits."""
     N, sharded, SquaredExp, Matern2, make_dataset, O = _mods()
     from friedrich_b200.synthetic import make_inputs
     d, q = 6, 300
@@ -68,6 +69,7 @@ def test_single_rank_sharded_fit_on_the_tcgen05_path_is_bitwise_equal_and_predic
     kd = SquaredExp(math.sqrt(d / 6.0), 1.0).device_desc()
     hs, hp = N.Handle(0), N.Handle(0)
     sharded.comm_init(hs, 0, 1)
+    assert N.lib().fgp_set_option(hs.ptr, N.FGP_OPT_SHARD_PIPE, pipe) == 0
     sharded.fit_sharded(hs, X, y, kd, 0.1)
     hp.check(N.lib().fgp_fit(hp.ptr, N.dptr(N.fcol(X)), n, n, d, N.dptr(y), C.byref(kd), 0.1, 0, 0.0))
     assert np.array_equal(np.tril(_factor(N, hs, n)), np.tril(_factor(N, hp, n)))
