@@ -229,7 +229,7 @@ def workload_config(workload, world, use_sharded, lookahead=True):
         desc = f"fit: Gram+Cholesky n={n} d={d} SquaredExp f64 sharded over {world} GPUs (n = 16384*N^(1/3)); predict q={q}"
     return n, d, q, {"workload": desc, "n": n, "d": d, "q": q, "noise": 0.1, "kernel": "SquaredExp(ls=sqrt(d/6), ampl=1)",
                      "l2": "inputs larger than L2 (factor = %.2f GB)" % (8.0 * n * n / 1e9),
-                     "multi_gpu": ("block-cyclic 512-column panels, NCCL panel broadcast, replicated factor; queries sharded")
+                     "multi_gpu": ("block-cyclic 512-column panels, each broadcast (NCCL) in row pieces so that solve / transfer / digit slicing / look-ahead overlap, replicated factor; queries sharded")
                      if use_sharded else "single GPU", "lookahead": lookahead}
 
 

@@ -14,6 +14,11 @@
 //
 // so the factorisation + broadcast of panel p+1 overlaps the trailing updates by panel p on all ranks, and when the loop
 // ends every rank holds the whole factor (replicated L: alpha solve and predict run locally, queries shard trivially).
+//
+// Three schedules share this distribution: factor_sharded (per-block-column chain of round 1, FGP_OPT_HEAD = 0),
+// factor_sharded_head (one head launch per panel, the panel broadcast in one piece, FGP_OPT_SHARD_PIPE = 0) and the default
+// factor_sharded_pipe at the end of this file (the panel travels in row pieces; solve / broadcast / slicing / look-ahead
+// overlap piece by piece).  All three produce the factor of the single-GPU schedule they mirror bit for bit.
 #include "ozaki.cuh"
 #include "sharded.cuh"
 
