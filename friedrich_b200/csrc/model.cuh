@@ -72,7 +72,7 @@ struct fgp_model {
     fgp::DevBuf Wp, Pscr, pbuf[2];
     fgp::DevBuf ozDigits, ozScale;         // base-128 digit slices + row scales of the panel being applied (csrc/ozaki.cuh)
     bool tcgen05 = true;                   // FGP_OPT_TCGEN05
-    bool shard_pipe = true;                // FGP_OPT_SHARD_PIPE: row-piece schedule of the multi-GPU fit
+    int shard_pipe = -1;                   // FGP_OPT_SHARD_PIPE: row-piece schedule of the multi-GPU fit (-1 = automatic: from 3 ranks up)
     fgp::DevBuf ozL, ozLscale;             // digit slices / row scales of EVERY panel of L with >= OZ_MIN_ROWS rows below it, kept by a
     std::vector<int64_t> ozOffBytes, ozOffRows;   // full single-GPU fit for the solves of predict: per panel byte / row offset, -1 = none
     bool ozL_valid = false;

@@ -178,9 +178,10 @@ int fgp_set_profiling(fgp_model* m, int on);
 /* FGP_OPT_TCGEN05 (default 1): trailing updates behind a panel with at least 1024 rows left run on the 5th-generation
  * tensor cores (tcgen05.mma kind::i8 on exact base-128 digit slices of the panel, int32 accumulators in TMEM; csrc/ozaki.cuh);
  * 0 = the f64 DMMA kernel everywhere (A/B runs; both meet the 1e-10 factor tolerance). */
-/* FGP_OPT_SHARD_PIPE (default 1): in the multi-GPU fit every panel travels in row pieces (solve, broadcast, digit slicing and the
- * next owner's look-ahead overlap piece by piece; csrc/sharded.cu factor_sharded_pipe); 0 = one piece per panel
- * (factor_sharded_head).  Same factor bit for bit.  The environment variable FGP_SHARD_PIPE=0 forces 0 for the whole process. */
+/* FGP_OPT_SHARD_PIPE (default -1 = automatic: 1 from 3 ranks up, else 0): 1 = in the multi-GPU fit every panel travels in row
+ * pieces (solve, broadcast, digit slicing and the next owner's look-ahead overlap piece by piece; csrc/sharded.cu
+ * factor_sharded_pipe); 0 = one piece per panel (factor_sharded_head; faster while the fit is work-bound, i.e. on 2 GPUs).
+ * Same factor bit for bit.  The environment variable FGP_SHARD_PIPE=0 forces 0 for the whole process. */
 enum fgp_option { FGP_OPT_LOOKAHEAD = 1, FGP_OPT_HEAD = 2, FGP_OPT_TCGEN05 = 3, FGP_OPT_SHARD_PIPE = 4 };
 int fgp_set_option(fgp_model* m, int option, int64_t value);
 int fgp_profile_summary(const fgp_model* m, double* ms, double* flops, int64_t* count);

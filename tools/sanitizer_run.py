@@ -55,6 +55,7 @@ if "--small" not in sys.argv:
     from friedrich_b200.kernels import SquaredExp  # noqa: E402
     hs = N.Handle(0)
     sharded.comm_init(hs, 0, 1)
+    assert N.lib().fgp_set_option(hs.ptr, N.FGP_OPT_SHARD_PIPE, 1) == 0   # (automatic = one piece below 3 ranks)
     kd = SquaredExp(0.8, 1.0).device_desc()
     sharded.fit_sharded(hs, X2, y2, kd, 0.1)
     mean, var = np.zeros(200), np.zeros(200)
