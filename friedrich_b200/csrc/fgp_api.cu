@@ -270,7 +270,7 @@ PairArgs query_pair_args(const fgp_model* m) {
 // the multi-RHS solve costs ~10 ms however few right-hand sides there are, a wavefront forward substitution per query 0.4 ms.
 //   Kc (np x q, one query per COLUMN) = k(train, query);  mean_i = Kc[:, i] . alpha;  z_i = L^-1 Kc[:, i] in place;
 //   var_i = k(q_i, q_i) - ||z_i||^2                                                            (mod.rs:235-241, :260-270)
-constexpr int64_t PREDICT_SMALL_Q = 12;  // measured at n = 16384: 0.45 ms (q = 1) .. 2.3 ms (q = 12); the tensor-pipe path: 2.5 ms
+constexpr int64_t PREDICT_SMALL_Q = 16;  // up to here ONE multi-right-hand-side wavefront launch; above, the tensor-pipe path (2.5 ms at n = 16384)
 static_assert(PREDICT_SMALL_Q <= TRSV_MULTI_QMAX, "latency path of predict: right-hand sides per wavefront launch");
 int predict_small(fgp_model* m, const fgp_kernel_desc* kd, const KernelTraits& kt, int want_mean, int want_var) {
     const int64_t qp = m->qp, np = m->np, q = m->q;

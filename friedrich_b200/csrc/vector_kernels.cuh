@@ -179,6 +179,28 @@ trsv_fwd_wave_kernel(const double* __restrict__ L, int64_t ld, const double* __r
 // wait) and applies it to every right-hand side; the x values are warp-uniform shared-memory broadcasts, the four column
 // quarters meet in shared memory.  (Per step and right-hand side the SM has 128 x 128 FMAs to do: 256 cycles at its fp64 rate.)
 constexpr int TRSV_MULTI_QMAX = 16;
+// One 128 x 128 tile (thread (r, h): row r, columns 32 h .. 32 h + 31 in v) applied to q right-hand sides in shared memory
+// (xs[j][128]); the four column quarters' partial sums go to red[j][h][r].  The x values are warp-uniform 16-byte broadcasts
+// (two per load: the loop is bound by shared-memory loads, not by the fp64 pipe); four accumulators per right-hand side as in
+// tile_apply_512.
+__device__ __forceinline__ void trsv_multi_apply(const double (&v)[32], const double* xs, double* red, int q, int r, int h) {
+#pragma unroll
+    for (int j = 0; j < TRSV_MULTI_QMAX; ++j) {
+        if (j < q) {
+            const double2* xj = reinterpret_cast<const double2*>(xs + j * 128 + 32 * h);
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+                const double2 x01 = xj[c >> 1], x23 = xj[(c >> 1) + 1];
+                a0 = fma(v[c], x01.x, a0);
+                a1 = fma(v[c + 1], x01.y, a1);
+                a2 = fma(v[c + 2], x23.x, a2);
+                a3 = fma(v[c + 3], x23.y, a3);
+            }
+            red[(j * 4 + h) * 128 + r] = (a0 + a1) + (a2 + a3);
+        }
+    }
+}
 constexpr int TRSV_MULTI_SMEM = TRSV_WAVE_SMEM + (TRSV_MULTI_QMAX * 128 + TRSV_MULTI_QMAX * 512) * 8;
 static __global__ void __launch_bounds__(TRSV_THREADS)
 trsv_fwd_wave_multi_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ inv, double* X, int64_t ldx, int q,
@@ -205,21 +227,7 @@ trsv_fwd_wave_multi_kernel(const double* __restrict__ L, int64_t ld, const doubl
         for (int idx = tid; idx < q * 128; idx += TRSV_THREADS)
             xs[idx] = __ldcg(X + (int64_t)jb * 128 + (idx & 127) + (int64_t)(idx >> 7) * ldx);
         __syncthreads();
-#pragma unroll
-        for (int j = 0; j < TRSV_MULTI_QMAX; ++j) {
-            if (j < q) {
-                const double* xj = xs + j * 128 + 32 * h;
-                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                    a0 = fma(v[c], xj[c], a0);
-                    a1 = fma(v[c + 1], xj[c + 1], a1);
-                    a2 = fma(v[c + 2], xj[c + 2], a2);
-                    a3 = fma(v[c + 3], xj[c + 3], a3);
-                }
-                red[(j * 4 + h) * 128 + r] = (a0 + a1) + (a2 + a3);
-            }
-        }
+        trsv_multi_apply(v, xs, red, q, r, h);
         __syncthreads();
         if (h == 0) {
 #pragma unroll
@@ -237,9 +245,24 @@ trsv_fwd_wave_multi_kernel(const double* __restrict__ L, int64_t ld, const doubl
         if (j < q && h == 0) xs[j * 128 + r] = acc[j];
     mbar_wait(bar, 0);
     __syncthreads();
-    for (int j = 0; j < q; ++j) {
-        const double sres = tile_apply_smem_512(inv_s, xs + j * 128, red);
-        if (tid < 128) X[row0 + tid + (int64_t)j * ldx] = sres;
+    // x_i = inv_i (...) for ALL right-hand sides in one pass: the tile's values once into registers, one barrier pair for the
+    // lot (a pass per right-hand side put 2 q barriers on every link of the wavefront chain); per right-hand side the same
+    // sums in the same order as tile_apply_smem_512
+    {
+        const double* p = inv_s + r + 32 * h * 128;
+        double w[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) w[c] = p[c * 128];
+        trsv_multi_apply(w, xs, red, q, r, h);
+        __syncthreads();
+        if (h == 0) {
+#pragma unroll
+            for (int j = 0; j < TRSV_MULTI_QMAX; ++j)
+                if (j < q) {
+                    const double* rj = red + j * 512 + r;
+                    X[row0 + r + (int64_t)j * ldx] = (rj[0] + rj[128]) + (rj[256] + rj[384]);
+                }
+        }
     }
     wave_publish(flags + i);
 }
